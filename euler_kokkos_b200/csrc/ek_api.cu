@@ -1,0 +1,550 @@
+// C ABI of libek_b200.so (include/ek_b200.h): context management, state transfer, ghost fill,
+// CFL time step, one fused step, and the sync-free time loop.  No CPU fallback: every entry point
+// that computes fails with EK_ERR_CUDA when there is no usable CUDA device.
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include "ek_internal.h"
+#include "boundary_kernels.cuh"
+
+using namespace ek;
+
+static thread_local std::string g_create_err;
+
+#define EK_CUDA(ctx, call)                                                                     \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess) {                                                                   \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                         \
+      return EK_ERR_CUDA;                                                                      \
+    }                                                                                          \
+  } while (0)
+
+// ---- tiny kernels of the device-resident time loop ---------------------------------------------
+// dt = cfl / invDt, clamped to t_end - t  (SolverHydroMuscl::compute_dt_local, SolverHydroMuscl.h:627;
+// SolverBase::compute_dt, shared/SolverBase.cpp:149-152).  Consumes and resets the running max.
+__global__ void pre_step_kernel(TimeState* ts, double cfl, int use_host_dt, double host_dt)
+{
+  if (ts->finished)
+    return;
+  double dt;
+  if (use_host_dt) {
+    dt = host_dt;
+  } else {
+    const double invdt = __longlong_as_double((long long)ts->invdt_bits);
+    dt = cfl / invdt;
+    if (ts->t + dt > ts->t_end)
+      dt = ts->t_end - ts->t;
+  }
+  ts->dt = dt;
+  ts->invdt_bits = 0ull;
+}
+
+// ++iteration; t += dt; finished? (SolverBase::next_iteration / finished, SolverBase.cpp:171-195)
+__global__ void post_step_kernel(TimeState* ts, int max_steps)
+{
+  if (ts->finished)
+    return;
+  ts->t += ts->dt;
+  ts->steps_done += 1;
+  if (ts->t >= ts->t_end - 1e-14 || ts->steps_done >= max_steps)
+    ts->finished = 1;
+}
+
+__global__ void reset_time_kernel(TimeState* ts, double t, double t_end)
+{
+  ts->t = t;
+  ts->t_end = t_end;
+  ts->steps_done = 0;
+  ts->finished = 0;
+}
+
+// ---- diagnostics ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) conserved_sums_kernel(const Grid g, const double* __restrict__ U, double* __restrict__ out)
+{
+  // one block per variable: deterministic tree sum (diagnostic, off the hot path)
+  const int v = blockIdx.x;
+  const long long ncell = (long long)g.nx * g.ny * g.nz;
+  double s = 0.0;
+  for (long long c = threadIdx.x; c < ncell; c += blockDim.x) {
+    const int i = (int)(c % g.nx) + g.gw;
+    const int j = (int)((c / g.nx) % g.ny) + g.gw;
+    const int k = (g.ksize > 1) ? (int)(c / ((long long)g.nx * g.ny)) + g.gw : 0;
+    s += U[i + g.sj * j + g.sk * k + g.sv * v];
+  }
+  __shared__ double red[256];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o)
+      red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0)
+    out[v] = red[0];
+}
+
+__global__ void __launch_bounds__(256) max_divb_kernel(const Grid g, const double* __restrict__ U, unsigned long long* __restrict__ out_bits)
+{
+  const long long ncell = (long long)g.nx * g.ny * g.nz;
+  double m = 0.0;
+  for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < ncell; c += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(c % g.nx) + g.gw;
+    const int j = (int)((c / g.nx) % g.ny) + g.gw;
+    const int k = (g.ksize > 1) ? (int)(c / ((long long)g.nx * g.ny)) + g.gw : 0;
+    const long long o = i + g.sj * j + g.sk * k;
+    double d = (U[o + 1 + g.sv * IA] - U[o + g.sv * IA]) / g.dx + (U[o + g.sj + g.sv * IB] - U[o + g.sv * IB]) / g.dy;
+    if (g.ksize > 1)
+      d += (U[o + g.sk + g.sv * IC] - U[o + g.sv * IC]) / g.dz;
+    m = fmax(m, fabs(d));
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0)
+    atomic_max_nonneg(out_bits, m);
+}
+
+// ---- helpers -------------------------------------------------------------------------------------
+static int validate(const ek_params& p, std::string& err)
+{
+  if (p.dim != 2 && p.dim != 3) { err = "dim must be 2 or 3"; return EK_ERR_INVALID; }
+  const int nbvar = p.mhd ? 8 : (p.dim == 3 ? 5 : 4);
+  const int gw = p.mhd ? 3 : 2;
+  if (p.nbvar != nbvar || p.ghost != gw) { err = "nbvar/ghost inconsistent with solver (HydroParams.cpp:94-115)"; return EK_ERR_INVALID; }
+  if (p.nx < gw || p.ny < gw || (p.dim == 3 && p.nz < gw)) { err = "interior sizes must be >= ghost width"; return EK_ERR_INVALID; }
+  if (p.dim == 2 && p.nz != 1) { err = "nz must be 1 in 2-D"; return EK_ERR_INVALID; }
+  if (!(p.dx > 0) || !(p.dy > 0) || (p.dim == 3 && !(p.dz > 0))) { err = "dx,dy,dz must be > 0"; return EK_ERR_INVALID; }
+  if (p.impl_version < 0 || p.impl_version > 2) { err = "implementationVersion must be 0,1,2"; return EK_ERR_INVALID; }
+  if (!p.mhd) {
+    const bool ok = p.riemann == EK_RIEMANN_APPROX || p.riemann == EK_RIEMANN_LLF || p.riemann == EK_RIEMANN_HLLC ||
+                    (p.riemann == EK_RIEMANN_HLL && p.dim == 2);
+    // the reference's 3-D dispatcher has no HLL branch and leaves the flux uninitialised
+    // (shared/RiemannSolvers.h:610-633); hlld is MHD-only
+    if (!ok) { err = "riemann solver not available for this hydro solver (RiemannSolvers.h:575-633)"; return EK_ERR_INVALID; }
+    if (!(p.slope_type == 0.0 || p.slope_type == 1.0 || p.slope_type == 2.0)) { err = "slope_type must be 0, 1 or 2"; return EK_ERR_INVALID; }
+  } else {
+    const bool ok = p.riemann == EK_RIEMANN_HLLD || p.riemann == EK_RIEMANN_HLL || p.riemann == EK_RIEMANN_LLF;
+    if (!ok) { err = "riemann solver not available for MHD (RiemannSolvers_MHD.h:371-389)"; return EK_ERR_INVALID; }
+    if (p.gravity_enabled) { err = "gravity is hydro-only in the reference"; return EK_ERR_INVALID; }
+  }
+  for (int f = 0; f < 6; ++f)
+    if (p.bc[f] < 0 || p.bc[f] > EK_BC_COPY) { err = "bad boundary type"; return EK_ERR_INVALID; }
+  return EK_OK;
+}
+
+static Grid make_grid(const ek_params& p)
+{
+  Grid g{};
+  g.nx = p.nx; g.ny = p.ny; g.nz = (p.dim == 3) ? p.nz : 1;
+  g.gw = p.ghost;
+  g.isize = p.nx + 2 * p.ghost;
+  g.jsize = p.ny + 2 * p.ghost;
+  g.ksize = (p.dim == 3) ? p.nz + 2 * p.ghost : 1;
+  g.nbvar = p.nbvar;
+  g.sj = g.isize;
+  g.sk = (long long)g.isize * g.jsize;
+  g.sv = g.sk * g.ksize;
+  g.dx = p.dx; g.dy = p.dy; g.dz = p.dz;
+  g.gamma0 = p.gamma0; g.gamma6 = p.gamma6; g.smallr = p.smallr; g.smallc = p.smallc;
+  g.smallp = p.smallp; g.smallpp = p.smallpp; g.cfl = p.cfl; g.slope_type = p.slope_type;
+  for (int f = 0; f < 6; ++f) g.bc[f] = p.bc[f];
+  g.impl_version = p.impl_version;
+  g.gravity_hancock = p.gravity_enabled && p.gravity_hancock;
+  return g;
+}
+
+static int blocks_for(long long n, int sm_count)
+{
+  long long b = (n + 255) / 256;
+  const long long cap = (long long)sm_count * 8;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+// physical BCs + halo exchange, X then Y then Z (SolverBase.cpp:464-512 serial, :583-664 MPI order)
+static int fill_boundaries(Ctx& c, double* U)
+{
+  const Grid& g = c.g;
+  const int ndir = (c.p.dim == 3) ? 3 : 2;
+  for (int d = 0; d < ndir; ++d) {
+    const bool any_copy = c.p.bc[2 * d] == EK_BC_COPY || c.p.bc[2 * d + 1] == EK_BC_COPY;
+    if (any_copy) {
+      int rc = comm_exchange_dir(c, U, d);
+      if (rc != EK_OK)
+        return rc;
+    }
+    if (c.p.bc[2 * d] == EK_BC_COPY && c.p.bc[2 * d + 1] == EK_BC_COPY)
+      continue;
+    const long long ext0 = (d == 0) ? 2 * g.gw : g.isize, ext1 = (d == 1) ? 2 * g.gw : g.jsize,
+                    ext2 = (d == 2) ? 2 * g.gw : g.ksize;
+    const int nb = blocks_for(ext0 * ext1 * ext2, c.sm_count);
+    if (d == 0)
+      fill_ghosts_kernel<0><<<nb, 256, 0, c.stream>>>(g, U, c.p.mhd, c.ts);
+    else if (d == 1)
+      fill_ghosts_kernel<1><<<nb, 256, 0, c.stream>>>(g, U, c.p.mhd, c.ts);
+    else
+      fill_ghosts_kernel<2><<<nb, 256, 0, c.stream>>>(g, U, c.p.mhd, c.ts);
+    c.launches++;
+    EK_CUDA(&c, cudaGetLastError());
+  }
+  return EK_OK;
+}
+
+// max invDt of the current level into ts->invdt_bits (+ max over ranks)
+static int prime_invdt(Ctx& c)
+{
+  EK_CUDA(&c, cudaMemsetAsync(&c.ts->invdt_bits, 0, sizeof(unsigned long long), c.stream));
+  if (c.p.mhd) {
+    int rc = fill_boundaries(c, c.U[c.cur]); // MHD dt reads primitives that need the upper ghost faces
+    if (rc != EK_OK)
+      return rc;
+    EK_CUDA(&c, launch_mhd_invdt(c, c.U[c.cur]));
+  } else {
+    EK_CUDA(&c, launch_hydro_invdt(c, c.U[c.cur]));
+  }
+  int rc = comm_allreduce_invdt(c);
+  if (rc != EK_OK)
+    return rc;
+  c.dt_primed = true;
+  return EK_OK;
+}
+
+// one godunov_unsplit on the stream; dt comes from the device (use_host_dt = 0) or from the host
+static int enqueue_step(Ctx& c, int use_host_dt, double host_dt, int max_steps)
+{
+  double* Uin = c.U[c.cur];
+  double* Uout = c.U[1 - c.cur];
+  if (c.p.mhd) {
+    // MHD: boundaries -> (prims) -> dt -> step   (SolverMHDMuscl.cpp:463-513)
+    int rc = fill_boundaries(c, Uin);
+    if (rc != EK_OK)
+      return rc;
+    if (!use_host_dt) {
+      EK_CUDA(&c, launch_mhd_invdt(c, Uin));
+      rc = comm_allreduce_invdt(c);
+      if (rc != EK_OK)
+        return rc;
+    }
+    pre_step_kernel<<<1, 1, 0, c.stream>>>(c.ts, c.p.cfl, use_host_dt, host_dt);
+    c.launches++;
+    ktime_mark(c);
+    EK_CUDA(&c, launch_mhd_step(c, Uin, Uout));
+    ktime_mark(c);
+  } else {
+    // hydro: dt (from the previous update's fused reduction) -> boundaries -> fused step
+    // (SolverHydroMuscl.h:637-679, SolverHydroMuscl.cpp:306-390)
+    if (!use_host_dt && !c.dt_primed) {
+      int rc = prime_invdt(c);
+      if (rc != EK_OK)
+        return rc;
+    }
+    pre_step_kernel<<<1, 1, 0, c.stream>>>(c.ts, c.p.cfl, use_host_dt, host_dt);
+    c.launches++;
+    int rc = fill_boundaries(c, Uin);
+    if (rc != EK_OK)
+      return rc;
+    ktime_mark(c);
+    EK_CUDA(&c, launch_hydro_step(c, Uin, Uout));
+    ktime_mark(c);
+    rc = comm_allreduce_invdt(c); // the fused reduction produced this rank's max for the next step
+    if (rc != EK_OK)
+      return rc;
+    c.dt_primed = true;
+  }
+  post_step_kernel<<<1, 1, 0, c.stream>>>(c.ts, max_steps);
+  c.launches++;
+  EK_CUDA(&c, cudaGetLastError());
+  return EK_OK;
+}
+
+// ---- ABI -----------------------------------------------------------------------------------------
+extern "C" {
+
+int ek_abi_version(void) { return EK_ABI_VERSION; }
+
+const char* ek_last_error(const ek_ctx* ctx)
+{
+  if (!ctx)
+    return g_create_err.c_str();
+  return reinterpret_cast<const Ctx*>(ctx)->err.c_str();
+}
+
+int ek_create(const ek_params* params, int device, ek_ctx** out)
+{
+  if (!params || !out) { g_create_err = "null argument"; return EK_ERR_INVALID; }
+  *out = nullptr;
+  int rc = validate(*params, g_create_err);
+  if (rc != EK_OK)
+    return rc;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_err = std::string("no CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU fallback";
+    return EK_ERR_CUDA;
+  }
+  if (device < 0 || device >= ndev) { g_create_err = "device index out of range"; return EK_ERR_INVALID; }
+  Ctx* c = new (std::nothrow) Ctx();
+  if (!c) { g_create_err = "out of host memory"; return EK_ERR_INVALID; }
+  c->p = *params;
+  c->g = make_grid(*params);
+  c->device = device;
+  c->state_len = c->g.sv * c->g.nbvar;
+#define CK(call)                                                                   \
+  do {                                                                             \
+    cudaError_t e2 = (call);                                                       \
+    if (e2 != cudaSuccess) {                                                       \
+      g_create_err = std::string(#call) + ": " + cudaGetErrorString(e2);           \
+      ek_destroy(reinterpret_cast<ek_ctx*>(c));                                    \
+      return EK_ERR_CUDA;                                                          \
+    }                                                                              \
+  } while (0)
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+  c->stream = c->own_stream;
+  CK(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming));
+  const size_t bytes = (size_t)c->state_len * sizeof(double);
+  CK(cudaMalloc(&c->U[0], bytes));
+  CK(cudaMalloc(&c->U[1], bytes));
+  CK(cudaMemset(c->U[0], 0, bytes));
+  CK(cudaMemset(c->U[1], 0, bytes));
+  if (params->gravity_enabled) {
+    CK(cudaMalloc(&c->grav, (size_t)c->g.sv * params->dim * sizeof(double)));
+    CK(cudaMemset(c->grav, 0, (size_t)c->g.sv * params->dim * sizeof(double)));
+  }
+  if (params->mhd) {
+    c->work_bytes = mhd_work_bytes(c->g);
+    if (c->work_bytes)
+      CK(cudaMalloc(&c->work, c->work_bytes));
+  }
+  CK(cudaMalloc(&c->ts, sizeof(TimeState)));
+  CK(cudaMemset(c->ts, 0, sizeof(TimeState)));
+  CK(cudaMallocHost(&c->ts_host, sizeof(TimeState)));
+  CK(cudaMalloc(&c->scratch, 64 * sizeof(double)));
+#undef CK
+  *out = reinterpret_cast<ek_ctx*>(c);
+  return EK_OK;
+}
+
+int ek_destroy(ek_ctx* ctx)
+{
+  if (!ctx)
+    return EK_OK;
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  cudaSetDevice(c->device);
+  ek_comm_detach(ctx);
+  for (cudaEvent_t e : c->kev) cudaEventDestroy(e);
+  if (c->own_stream) cudaStreamSynchronize(c->own_stream);
+  cudaFree(c->U[0]); cudaFree(c->U[1]); cudaFree(c->grav); cudaFree(c->work); cudaFree(c->ts); cudaFree(c->scratch);
+  if (c->ts_host) cudaFreeHost(c->ts_host);
+  if (c->ev_a) cudaEventDestroy(c->ev_a);
+  if (c->ev_b) cudaEventDestroy(c->ev_b);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
+  delete c;
+  return EK_OK;
+}
+
+int ek_set_stream(ek_ctx* ctx, void* cuda_stream)
+{
+  if (!ctx) return EK_ERR_INVALID;
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  c->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+  return EK_OK;
+}
+
+int ek_sync(ek_ctx* ctx)
+{
+  if (!ctx) return EK_ERR_INVALID;
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  EK_CUDA(c, cudaSetDevice(c->device));
+  EK_CUDA(c, cudaStreamSynchronize(c->stream));
+  return EK_OK;
+}
+
+int64_t ek_state_len(const ek_ctx* ctx) { return ctx ? reinterpret_cast<const Ctx*>(ctx)->state_len : 0; }
+int64_t ek_launch_count(const ek_ctx* ctx) { return ctx ? reinterpret_cast<const Ctx*>(ctx)->launches : 0; }
+
+int ek_upload_state(ek_ctx* ctx, const double* U_host)
+{
+  if (!ctx || !U_host) return EK_ERR_INVALID;
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  EK_CUDA(c, cudaSetDevice(c->device));
+  const size_t bytes = (size_t)c->state_len * sizeof(double);
+  c->cur = 0;
+  EK_CUDA(c, cudaMemcpyAsync(c->U[0], U_host, bytes, cudaMemcpyHostToDevice, c->stream));
+  EK_CUDA(c, cudaMemcpyAsync(c->U[1], c->U[0], bytes, cudaMemcpyDeviceToDevice, c->stream));
+  c->dt_primed = false;
+  EK_CUDA(c, cudaStreamSynchronize(c->stream)); // the host buffer may be pageable / reused
+  return EK_OK;
+}
+
+int ek_download_state(ek_ctx* ctx, double* U_host)
+{
+  if (!ctx || !U_host) return EK_ERR_INVALID;
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  EK_CUDA(c, cudaSetDevice(c->device));
+  EK_CUDA(c, cudaMemcpyAsync(U_host, c->U[c->cur], (size_t)c->state_len * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  EK_CUDA(c, cudaStreamSynchronize(c->stream));
+  return EK_OK;
+}
+
+int ek_device_state(ek_ctx* ctx, double** dptr)
+{
+  if (!ctx || !dptr) return EK_ERR_INVALID;
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  *dptr = c->U[c->cur];
+  c->dt_primed = false; // the caller may modify the state through this pointer
+  return EK_OK;
+}
+
+int ek_set_gravity(ek_ctx* ctx, const double* g_host)
+{
+  if (!ctx || !g_host) return EK_ERR_INVALID;
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  if (!c->grav) { c->err = "gravity not enabled in ek_params"; return EK_ERR_STATE; }
+  EK_CUDA(c, cudaSetDevice(c->device));
+  EK_CUDA(c, cudaMemcpyAsync(c->grav, g_host, (size_t)c->g.sv * c->p.dim * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  EK_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->dt_primed = false;
+  return EK_OK;
+}
+
+int ek_fill_boundaries(ek_ctx* ctx)
+{
+  if (!ctx) return EK_ERR_INVALID;
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  EK_CUDA(c, cudaSetDevice(c->device));
+  // not part of a device-resident loop: never skipped by the 'finished' flag
+  EK_CUDA(c, cudaMemsetAsync(&c->ts->finished, 0, sizeof(int), c->stream));
+  return fill_boundaries(*c, c->U[c->cur]);
+}
+
+int ek_compute_dt(ek_ctx* ctx, double* dt_out)
+{
+  if (!ctx || !dt_out) return EK_ERR_INVALID;
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  EK_CUDA(c, cudaSetDevice(c->device));
+  EK_CUDA(c, cudaMemsetAsync(&c->ts->finished, 0, sizeof(int), c->stream));
+  if (!c->dt_primed || c->p.mhd) {
+    int rc = prime_invdt(*c);
+    if (rc != EK_OK)
+      return rc;
+  }
+  EK_CUDA(c, cudaMemcpyAsync(c->ts_host, c->ts, sizeof(TimeState), cudaMemcpyDeviceToHost, c->stream));
+  EK_CUDA(c, cudaStreamSynchronize(c->stream));
+  double invdt;
+  memcpy(&invdt, &c->ts_host->invdt_bits, sizeof(double));
+  *dt_out = c->p.cfl / invdt;
+  return EK_OK;
+}
+
+int ek_step(ek_ctx* ctx, double dt)
+{
+  if (!ctx) return EK_ERR_INVALID;
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  EK_CUDA(c, cudaSetDevice(c->device));
+  reset_time_kernel<<<1, 1, 0, c->stream>>>(c->ts, 0.0, 1e300);
+  c->launches++;
+  int rc = enqueue_step(*c, 1, dt, 1 << 30);
+  if (rc != EK_OK)
+    return rc;
+  c->cur = 1 - c->cur;
+  return EK_OK;
+}
+
+int ek_run(ek_ctx* ctx, int nsteps, double t, double t_end, double* t_out, double* dt_last_out, int* steps_done_out)
+{
+  if (!ctx || nsteps < 0) return EK_ERR_INVALID;
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  EK_CUDA(c, cudaSetDevice(c->device));
+  reset_time_kernel<<<1, 1, 0, c->stream>>>(c->ts, t, t_end);
+  c->launches++;
+  // SolverBase::finished() is evaluated before the first iteration too
+  if (t >= t_end - 1e-14)
+    nsteps = 0;
+  for (int s = 0; s < nsteps; ++s) {
+    int rc = enqueue_step(*c, 0, 0.0, nsteps);
+    if (rc != EK_OK)
+      return rc;
+    c->cur = 1 - c->cur; // provisional; corrected below if the loop finished early on the device
+  }
+  EK_CUDA(c, cudaMemcpyAsync(c->ts_host, c->ts, sizeof(TimeState), cudaMemcpyDeviceToHost, c->stream));
+  EK_CUDA(c, cudaStreamSynchronize(c->stream));
+  const int done = c->ts_host->steps_done;
+  if (((nsteps - done) & 1) != 0)
+    c->cur = 1 - c->cur; // skipped steps did not flip the levels
+  if (done < nsteps)
+    c->dt_primed = false; // skipped steps consumed nothing, but be conservative
+  if (t_out) *t_out = c->ts_host->t;
+  if (dt_last_out) *dt_last_out = c->ts_host->dt;
+  if (steps_done_out) *steps_done_out = done;
+  return EK_OK;
+}
+
+int ek_kernel_timing(ek_ctx* ctx, int enable)
+{
+  if (!ctx) return EK_ERR_INVALID;
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  for (cudaEvent_t e : c->kev) cudaEventDestroy(e);
+  c->kev.clear();
+  c->ktiming = enable != 0;
+  return EK_OK;
+}
+
+int ek_kernel_time(ek_ctx* ctx, double* total_ms_out, int* launches_out)
+{
+  if (!ctx || !total_ms_out || !launches_out) return EK_ERR_INVALID;
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  EK_CUDA(c, cudaSetDevice(c->device));
+  EK_CUDA(c, cudaStreamSynchronize(c->stream));
+  double tot = 0.0;
+  int n = 0;
+  for (size_t i = 0; i + 1 < c->kev.size(); i += 2) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->kev[i], c->kev[i + 1]) == cudaSuccess) {
+      tot += ms;
+      ++n;
+    }
+  }
+  for (cudaEvent_t e : c->kev) cudaEventDestroy(e);
+  c->kev.clear();
+  *total_ms_out = tot;
+  *launches_out = n;
+  return EK_OK;
+}
+
+int ek_conserved_sums(ek_ctx* ctx, double* sums_out)
+{
+  if (!ctx || !sums_out) return EK_ERR_INVALID;
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  EK_CUDA(c, cudaSetDevice(c->device));
+  conserved_sums_kernel<<<c->g.nbvar, 256, 0, c->stream>>>(c->g, c->U[c->cur], c->scratch);
+  c->launches++;
+  int rc = comm_allreduce_sum(*c, c->scratch, c->g.nbvar);
+  if (rc != EK_OK) return rc;
+  EK_CUDA(c, cudaMemcpyAsync(sums_out, c->scratch, c->g.nbvar * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  EK_CUDA(c, cudaStreamSynchronize(c->stream));
+  return EK_OK;
+}
+
+int ek_max_divb(ek_ctx* ctx, double* out)
+{
+  if (!ctx || !out) return EK_ERR_INVALID;
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  if (!c->p.mhd) { c->err = "ek_max_divb: MHD only"; return EK_ERR_STATE; }
+  EK_CUDA(c, cudaSetDevice(c->device));
+  EK_CUDA(c, cudaMemsetAsync(c->scratch, 0, sizeof(double), c->stream));
+  const long long ncell = (long long)c->g.nx * c->g.ny * c->g.nz;
+  max_divb_kernel<<<blocks_for(ncell, c->sm_count), 256, 0, c->stream>>>(c->g, c->U[c->cur], reinterpret_cast<unsigned long long*>(c->scratch));
+  c->launches++;
+  int rc = comm_allreduce_max(*c, c->scratch, 1);
+  if (rc != EK_OK) return rc;
+  EK_CUDA(c, cudaMemcpyAsync(out, c->scratch, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  EK_CUDA(c, cudaStreamSynchronize(c->stream));
+  return EK_OK;
+}
+
+} // extern "C"

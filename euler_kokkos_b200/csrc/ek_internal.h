@@ -1,0 +1,70 @@
+// Internal (non-ABI) declarations shared by the translation units of libek_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+#include "../../include/ek_b200.h"
+#include "ek_common.cuh"
+
+namespace ek {
+
+struct NcclApi; // ek_comm.cu
+
+struct Ctx {
+  ek_params p{};
+  Grid g{};
+  int device = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;      // own_stream or caller-provided
+  cudaStream_t comm_stream = nullptr; // halo exchange
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  double* U[2] = { nullptr, nullptr }; // ping-pong levels
+  int cur = 0;                         // index of the current level
+  double* grav = nullptr;
+  double* work = nullptr;   // solver scratch (MHD: staged arrays)
+  size_t work_bytes = 0;
+  TimeState* ts = nullptr;  // device
+  TimeState* ts_host = nullptr; // pinned
+  double* scratch = nullptr; // small device scratch for diagnostics (>= 64 doubles)
+  int64_t state_len = 0;
+  int64_t launches = 0;
+  bool dt_primed = false; // ts->invdt_bits holds max invDt of the current level
+  int sm_count = 148;
+  // communicator (z-slab / cartesian neighbours)
+  void* nccl_comm = nullptr;
+  int rank = 0, nranks = 1;
+  int neighbor[6] = { -1, -1, -1, -1, -1, -1 };
+  double* halo_send[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+  double* halo_recv[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+  // optional event pairs around the dominant kernel (ek_kernel_timing)
+  bool ktiming = false;
+  std::vector<cudaEvent_t> kev; // start/stop pairs recorded so far
+  std::string err;
+};
+
+// record an event on the context's stream when kernel timing is enabled
+inline void ktime_mark(Ctx& c)
+{
+  if (!c.ktiming)
+    return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess)
+    return;
+  cudaEventRecord(e, c.stream);
+  c.kev.push_back(e);
+}
+
+// hydro_launch.cu
+cudaError_t launch_hydro_step(Ctx& c, const double* Uin, double* Uout);
+cudaError_t launch_hydro_invdt(Ctx& c, const double* U);
+// mhd_launch.cu
+cudaError_t launch_mhd_step(Ctx& c, const double* Uin, double* Uout);
+cudaError_t launch_mhd_invdt(Ctx& c, const double* U);
+size_t mhd_work_bytes(const Grid& g);
+// ek_comm.cu
+int comm_exchange_dir(Ctx& c, double* U, int dir);       // halo exchange along one direction
+int comm_allreduce_invdt(Ctx& c);                        // max over ranks of ts->invdt_bits
+int comm_allreduce_sum(Ctx& c, double* dev_vals, int n); // diagnostics
+int comm_allreduce_max(Ctx& c, double* dev_vals, int n);
+
+} // namespace ek

@@ -1,0 +1,99 @@
+// Small extern "C" surface of the C++ host layer, so that bench.py and the Python tests go through
+// the SAME ini parsing, parameter derivation, decomposition and initial conditions as euler_b200.
+#include <cstring>
+#include <fstream>
+#include <string>
+
+#include "ConfigMap.h"
+#include "HydroParams.h"
+#include "InitConditions.h"
+#include "SolverFactory.h"
+
+namespace euler_b200 {
+int run_ini(const std::string& input_file, const std::string& overrides);
+
+struct HostCase {
+  ConfigMap configMap;
+  ParallelEnv env;
+  HydroParams* params = nullptr;
+  ~HostCase() { delete params; }
+};
+} // namespace euler_b200
+
+using namespace euler_b200;
+
+extern "C" {
+
+// overrides: "section.name=value" lines.  Returns nullptr if the file cannot be read.
+void* ekh_case_create(const char* ini_path, const char* overrides, int rank, int nranks)
+{
+  HostCase* c = new HostCase();
+  c->configMap = ConfigMap(ini_path);
+  if (c->configMap.ParseError() < 0) {
+    delete c;
+    return nullptr;
+  }
+  if (overrides)
+    c->configMap.applyOverrides(overrides);
+  c->env.rank = rank;
+  c->env.nranks = nranks;
+  c->params = new HydroParams(c->configMap, c->env);
+  return c;
+}
+void ekh_case_destroy(void* h) { delete static_cast<HostCase*>(h); }
+
+int ekh_case_params(void* h, ek_params* out)
+{
+  if (!h || !out) return 1;
+  *out = static_cast<HostCase*>(h)->params->to_ek_params();
+  return 0;
+}
+int ekh_case_neighbors(void* h, int32_t* nb6)
+{
+  if (!h || !nb6) return 1;
+  for (int f = 0; f < 6; ++f) nb6[f] = static_cast<HostCase*>(h)->params->neighborsRank[f];
+  return 0;
+}
+// run scalars: out[0]=tEnd, out[1]=nStepmax, out[2]=nOutput, out[3]=nlog, out[4]=xmin, out[5]=ymin, out[6]=zmin,
+// out[7..9]=mpi pos, out[10..12]=mx,my,mz
+int ekh_case_run_info(void* h, double* out)
+{
+  if (!h || !out) return 1;
+  const HydroParams& p = *static_cast<HostCase*>(h)->params;
+  out[0] = p.tEnd; out[1] = p.nStepmax; out[2] = p.nOutput; out[3] = p.nlog; out[4] = p.xmin; out[5] = p.ymin; out[6] = p.zmin;
+  out[7] = p.myMpiPos[0]; out[8] = p.myMpiPos[1]; out[9] = p.myMpiPos[2]; out[10] = p.mx; out[11] = p.my; out[12] = p.mz;
+  return 0;
+}
+int ekh_case_get_string(void* h, const char* section, const char* name, char* out, int cap)
+{
+  if (!h || !out || cap <= 0) return 1;
+  const std::string v = static_cast<HostCase*>(h)->configMap.getString(section, name, "");
+  std::strncpy(out, v.c_str(), cap - 1);
+  out[cap - 1] = 0;
+  return 0;
+}
+double ekh_case_get_float(void* h, const char* section, const char* name, float dflt)
+{
+  return static_cast<HostCase*>(h)->configMap.getFloat(section, name, dflt);
+}
+// U (and grav, may be null) must be zero-filled, sized for the ghosted local box
+int ekh_case_init_state(void* h, double* U, double* grav)
+{
+  if (!h || !U) return 1;
+  HostCase* c = static_cast<HostCase*>(h);
+  const std::string problem = c->configMap.getString("hydro", "problem", "unknown");
+  return init_problem(problem, *c->params, c->configMap, U, grav) ? 0 : 2;
+}
+int ekh_case_write_ini(void* h, const char* path)
+{
+  if (!h || !path) return 1;
+  std::ofstream f(path);
+  if (!f) return 2;
+  f << static_cast<HostCase*>(h)->configMap.toIni();
+  return 0;
+}
+int ekh_solver_registered(const char* name) { return SolverFactory::Instance().has(name) ? 1 : 0; }
+// the whole driver (main.cpp) as a function
+int ekh_run_ini(const char* ini_path, const char* overrides) { return run_ini(ini_path, overrides ? overrides : ""); }
+
+} // extern "C"

@@ -1,0 +1,394 @@
+// Fused Euler MUSCL-Hancock step for sm_100a: cons->prim, limited slopes, Hancock trace, Riemann
+// fluxes, conservative update, gravity source term and the next step's CFL reduction in ONE kernel.
+//
+// Replaces, per time step, the reference's ConvertToPrimitivesFunctor3D + ComputeAndStoreFluxesFunctor3D
+// + UpdateFunctor3D (+ GravitySourceTermFunctor3D + ComputeDtFunctor3D) and the deep_copy(U2,U)
+// (muscl/SolverHydroMuscl.cpp:306-390, muscl/HydroRunFunctors3D.h:16-820,1903-1985): the conserved
+// state is read once and written once; Q, the three flux arrays and the slopes never exist in HBM.
+//
+// Tiling ("2.5-D z-march"): a CTA owns a TX x TY column of interior cells (TX = 28 so that the
+// tile + 2-cell halo is exactly one 32-lane warp wide; one warp per tile row, TY+4 warps) and
+// marches along z over a chunk of planes.  Per plane the z-neighbours of a cell live in the
+// registers of the thread that owns the column; x/y neighbours are exchanged through shared memory.
+// Every Riemann problem is solved once per face (by the thread of the upper cell), every slope and
+// trace once per cell; only the 1-cell ring around the tile is computed redundantly.
+#pragma once
+#include "hydro_physics.cuh"
+
+namespace ek {
+
+constexpr int HTX = 28; // interior cells per tile row (tile + halo 2 = 32 lanes)
+
+template <int DIM, int TY>
+struct HydroSmem {
+  static constexpr int NV = HydroTraits<DIM>::NV;
+  static constexpr int ROWS = TY + 4;
+  static constexpr int PLANE = ROWS * 32; // doubles per variable
+  double q[NV * PLANE];   // primitives of the current plane
+  double mx[NV * PLANE];  // state on the XMAX face of each cell (left state of face i+1)
+  double my[NV * PLANE];  // state on the YMAX face of each cell
+  double fx[NV * PLANE];  // flux*dt/dx through the lower x face of each cell
+  double fy[NV * PLANE];  // flux*dt/dy through the lower y face of each cell
+  double red[ROWS];       // per-warp invDt maxima
+};
+
+struct HydroArgs {
+  Grid g;
+  const double* __restrict__ Uin;
+  double* __restrict__ Uout;
+  const double* __restrict__ grav; // [DIM][k][j][i] or nullptr
+  TimeState* ts;
+  int zchunk; // planes per CTA along z (3-D)
+};
+
+template <int DIM, int RS, int TY, bool GRAV>
+__global__ void __launch_bounds__(32 * (TY + 4), 1) hydro_step_kernel(const HydroArgs a)
+{
+  constexpr int NV = HydroTraits<DIM>::NV;
+  using Smem = HydroSmem<DIM, TY>;
+  constexpr int PLANE = Smem::PLANE;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+
+  const Grid& g = a.g;
+  if (a.ts->finished)
+    return;
+  const double dt = a.ts->dt;
+  const double dtd[3] = { dt / g.dx, dt / g.dy, (DIM == 3) ? dt / g.dz : 0.0 };
+
+  const int lane = threadIdx.x, row = threadIdx.y;
+  const int xg = g.gw + blockIdx.x * HTX + lane - 2; // ghosted coordinates of this thread's column
+  const int yg = g.gw + blockIdx.y * TY + row - 2;
+  const int so = row * 32 + lane; // offset inside one smem variable plane
+
+  const bool inb = (xg < g.isize) && (yg < g.jsize);
+  // cells whose slopes/trace are needed: the tile plus a 1-cell ring (inside the ghosted box)
+  const bool do_trace = inb && lane >= 1 && lane <= 30 && row >= 1 && row <= TY + 2 && xg <= g.nx + g.gw &&
+                        yg <= g.ny + g.gw;
+  const bool in_x = lane >= 2 && lane <= 29 && xg < g.nx + g.gw; // interior column range of the tile
+  const bool in_y = row >= 2 && row <= TY + 1 && yg < g.ny + g.gw;
+  const bool do_fx = inb && lane >= 2 && lane <= 30 && xg <= g.nx + g.gw && in_y; // lower x faces
+  const bool do_fy = inb && in_x && row >= 2 && row <= TY + 2 && yg <= g.ny + g.gw;
+  const bool do_cell = in_x && in_y;
+
+  const long long col = (long long)xg + g.sj * (long long)yg;
+  const double* __restrict__ Uin = a.Uin;
+
+  auto load_prims = [&](int k, double* q) {
+    if (inb) {
+      double u[NV], rd;
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+        u[v] = __ldg(Uin + col + g.sk * k + g.sv * v);
+      hydro_cons_to_prim<DIM>(g, u, q, rd);
+    } else {
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+        q[v] = 1.0;
+    }
+  };
+
+  int kbeg = 0, kend = 1;
+  if constexpr (DIM == 3) {
+    kbeg = g.gw + blockIdx.z * a.zchunk;
+    kend = min(kbeg + a.zchunk, g.nz + g.gw);
+  }
+
+  double qprev[NV], qcur[NV], qnext[NV]; // z pipeline of primitives (3-D)
+  double mzprev[NV];                     // ZMAX-face state of the previous plane
+  double part[NV];                       // U + fx - fx' + fy - fy' + fz of the previous plane
+  double invdt = 0.0;
+
+  if constexpr (DIM == 3) {
+    load_prims(kbeg - 2, qprev);
+    load_prims(kbeg - 1, qcur);
+    load_prims(kbeg, qnext);
+  } else {
+    load_prims(0, qcur);
+  }
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    mzprev[v] = 1.0;
+    part[v] = 0.0;
+  }
+
+  const int pbeg = (DIM == 3) ? kbeg - 1 : 0;
+  const int pend = (DIM == 3) ? kend : 0; // inclusive
+
+  for (int p = pbeg; p <= pend; ++p) {
+    // -- prefetch the conserved state two planes ahead (consumed at the bottom of the loop)
+    double unext[NV];
+    const bool have_next = (DIM == 3) && (p + 2 <= kend + 1) && inb;
+    if (have_next) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+        unext[v] = __ldg(Uin + col + g.sk * (p + 2) + g.sv * v);
+    }
+
+    // -- publish primitives of plane p
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+      sm.q[v * PLANE + so] = qcur[v];
+    __syncthreads();
+
+    // -- slopes + Hancock trace of this cell
+    double px[NV], py[NV], pz[NV], mz[NV]; // states on the XMIN, YMIN, ZMIN, ZMAX faces
+    if (do_trace) {
+      double dq[3][5];
+      const double st = g.slope_type;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const double qc = qcur[v];
+        dq[0][v] = limited_slope(st, sm.q[v * PLANE + so - 1], qc, sm.q[v * PLANE + so + 1]);
+        dq[1][v] = limited_slope(st, sm.q[v * PLANE + so - 32], qc, sm.q[v * PLANE + so + 32]);
+        if constexpr (DIM == 3)
+          dq[2][v] = limited_slope(st, qprev[v], qc, qnext[v]);
+      }
+      if (st == 0.0) { // slope_type 0: first-order (HydroBaseFunctor3D.h:498-520)
+#pragma unroll
+        for (int d = 0; d < DIM; ++d)
+#pragma unroll
+          for (int v = 0; v < NV; ++v)
+            dq[d][v] = 0.0;
+      }
+      double s[NV];
+      hydro_sources<DIM>(g, qcur, dq, s);
+      double gh[3] = { 0.0, 0.0, 0.0 }; // gravity predictor 0.5*dt*g on the velocities
+      if constexpr (GRAV) {
+        if (g.gravity_hancock) {
+#pragma unroll
+          for (int c = 0; c < DIM; ++c)
+            gh[c] = 0.5 * dt * __ldg(a.grav + col + g.sk * p + g.sv * c);
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const double add = (v >= IU) ? gh[v - IU] : 0.0;
+        const double sx = s[v] * (dtd[0] * 0.5), sy = s[v] * (dtd[1] * 0.5);
+        const double hx = 0.5 * dq[0][v], hy = 0.5 * dq[1][v];
+        px[v] = (qcur[v] - hx) + sx + add;
+        py[v] = (qcur[v] - hy) + sy + add;
+        double mxv = (qcur[v] + hx) + sx + add;
+        double myv = (qcur[v] + hy) + sy + add;
+        if (v == ID) {
+          px[v] = dmax(g.smallr, px[v]);
+          py[v] = dmax(g.smallr, py[v]);
+          mxv = dmax(g.smallr, mxv);
+          myv = dmax(g.smallr, myv);
+        }
+        sm.mx[v * PLANE + so] = mxv;
+        sm.my[v * PLANE + so] = myv;
+        if constexpr (DIM == 3) {
+          const double sz = s[v] * (dtd[2] * 0.5);
+          const double hz = 0.5 * dq[2][v];
+          // implementationVersion 1 omits the gravity predictor on the ZMIN-face state
+          // (HydroRunFunctors3D.h:1351 vs :1277-1285)
+          const double addz = (g.impl_version == 1) ? 0.0 : add;
+          pz[v] = (qcur[v] - hz) + sz + addz;
+          mz[v] = (qcur[v] + hz) + sz + add;
+          if (v == ID) {
+            pz[v] = dmax(g.smallr, pz[v]);
+            mz[v] = dmax(g.smallr, mz[v]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+
+    // -- Riemann problems at the lower x / y / z faces of this cell
+    double fxl[NV], fyl[NV], fzl[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+      fxl[v] = fyl[v] = fzl[v] = 0.0;
+    if (do_fx) {
+      double ql[NV];
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+        ql[v] = sm.mx[v * PLANE + so - 1];
+      riemann_hydro<DIM, RS>(g, ql, px, fxl);
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        fxl[v] *= dtd[0];
+        sm.fx[v * PLANE + so] = fxl[v];
+      }
+    }
+    if (do_fy) {
+      double ql[NV], qr[NV], f[NV];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        ql[v] = sm.my[v * PLANE + so - 32];
+        qr[v] = py[v];
+      }
+      // rotate: normal velocity first
+      { double t = ql[IU]; ql[IU] = ql[IV]; ql[IV] = t; }
+      { double t = qr[IU]; qr[IU] = qr[IV]; qr[IV] = t; }
+      riemann_hydro<DIM, RS>(g, ql, qr, f);
+      { double t = f[IU]; f[IU] = f[IV]; f[IV] = t; }
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        fyl[v] = f[v] * dtd[1];
+        sm.fy[v * PLANE + so] = fyl[v];
+      }
+    }
+    if constexpr (DIM == 3) {
+      if (do_cell) { // face between plane p-1 and p (p-1 >= kbeg-1 has been traced, except at p == pbeg)
+        if (p > pbeg) {
+          double ql[NV], qr[NV], f[NV];
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            ql[v] = mzprev[v];
+            qr[v] = pz[v];
+          }
+          { double t = ql[IU]; ql[IU] = ql[IW]; ql[IW] = t; }
+          { double t = qr[IU]; qr[IU] = qr[IW]; qr[IW] = t; }
+          riemann_hydro<DIM, RS>(g, ql, qr, f);
+          { double t = f[IU]; f[IU] = f[IW]; f[IW] = t; }
+#pragma unroll
+          for (int v = 0; v < NV; ++v)
+            fzl[v] = f[v] * dtd[2];
+        }
+      }
+    }
+    __syncthreads();
+
+    // -- finish plane p-1 (3-D) / plane p (2-D), start the accumulation of plane p
+    if (do_cell) {
+      if constexpr (DIM == 3) {
+        if (p - 1 >= kbeg) {
+          double un[NV];
+#pragma unroll
+          for (int v = 0; v < NV; ++v)
+            un[v] = part[v] - fzl[v];
+          const long long o = col + g.sk * (p - 1);
+          double gv[3] = { 0.0, 0.0, 0.0 };
+          if constexpr (GRAV) {
+            // GravitySourceTermFunctor3D (HydroRunFunctors3D.h:1939-1975)
+            const double rhoOld = __ldg(Uin + o);
+            const double rhoNew = un[ID];
+            const double ir = 1.0 / rhoNew;
+            const double ek0 = 0.5 * (un[IU] * un[IU] + un[IV] * un[IV] + un[IW] * un[IW]) * ir;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              gv[c] = __ldg(a.grav + o + g.sv * c);
+              un[IU + c] += 0.5 * dt * gv[c] * (rhoOld + rhoNew);
+            }
+            const double ek1 = 0.5 * (un[IU] * un[IU] + un[IV] * un[IV] + un[IW] * un[IW]) * ir;
+            un[IP] += (ek1 - ek0);
+          }
+#pragma unroll
+          for (int v = 0; v < NV; ++v)
+            a.Uout[o + g.sv * v] = un[v];
+          invdt = dmax(invdt, hydro_cell_invdt<DIM, GRAV>(g, un, gv));
+        }
+        if (p < kend) {
+          const long long o = col + g.sk * p;
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            double u = __ldg(Uin + o + g.sv * v);
+            u += fxl[v];
+            u -= sm.fx[v * PLANE + so + 1];
+            u += fyl[v];
+            u -= sm.fy[v * PLANE + so + 32];
+            u += fzl[v];
+            part[v] = u;
+          }
+        }
+      } else {
+        double un[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          double u = __ldg(Uin + col + g.sv * v);
+          u += fxl[v];
+          u -= sm.fx[v * PLANE + so + 1];
+          u += fyl[v];
+          u -= sm.fy[v * PLANE + so + 32];
+          un[v] = u;
+        }
+        double gv[3] = { 0.0, 0.0, 0.0 };
+        if constexpr (GRAV) {
+          // GravitySourceTermFunctor2D (HydroRunFunctors2D.h:1594-1625): rhoNew floored at smallr
+          const double rhoOld = __ldg(Uin + col);
+          const double rhoNew = dmax(g.smallr, un[ID]);
+          const double ir = 1.0 / rhoNew;
+          const double ek0 = 0.5 * (un[IU] * un[IU] + un[IV] * un[IV]) * ir;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            gv[c] = __ldg(a.grav + col + g.sv * c);
+            un[IU + c] += 0.5 * dt * gv[c] * (rhoOld + rhoNew);
+          }
+          const double ek1 = 0.5 * (un[IU] * un[IU] + un[IV] * un[IV]) * ir;
+          un[IP] += (ek1 - ek0);
+        }
+#pragma unroll
+        for (int v = 0; v < NV; ++v)
+          a.Uout[col + g.sv * v] = un[v];
+        invdt = dmax(invdt, hydro_cell_invdt<DIM, GRAV>(g, un, gv));
+      }
+    }
+
+    // -- rotate the z pipeline
+    if constexpr (DIM == 3) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        qprev[v] = qcur[v];
+        qcur[v] = qnext[v];
+        mzprev[v] = mz[v];
+      }
+      if (have_next) {
+        double rd;
+        hydro_cons_to_prim<DIM>(g, unext, qnext, rd);
+      }
+    }
+  }
+
+  // -- CFL reduction for the NEXT step: warp shuffles, then one atomic per CTA (grid reduce)
+  invdt = warp_max(invdt);
+  if (lane == 0)
+    sm.red[row] = invdt;
+  __syncthreads();
+  if (row == 0) {
+    double m = (lane < TY + 4) ? sm.red[lane] : 0.0;
+    m = warp_max(m);
+    if (lane == 0)
+      atomic_max_nonneg(&a.ts->invdt_bits, m);
+  }
+}
+
+// Stand-alone CFL reduction (first step, ek_compute_dt): ComputeDtFunctor{2D,3D} / Gravity variant.
+template <int DIM, bool GRAV>
+__global__ void __launch_bounds__(256) hydro_invdt_kernel(const Grid g, const double* __restrict__ U, const double* __restrict__ grav,
+                                                          unsigned long long* __restrict__ out_bits)
+{
+  constexpr int NV = HydroTraits<DIM>::NV;
+  const long long ncell = (long long)g.nx * g.ny * g.nz;
+  double m = 0.0;
+  for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < ncell; c += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(c % g.nx) + g.gw;
+    const int j = (int)((c / g.nx) % g.ny) + g.gw;
+    const int k = (DIM == 3) ? (int)(c / ((long long)g.nx * g.ny)) + g.gw : 0;
+    const long long o = i + g.sj * j + g.sk * k;
+    double u[NV], gv[3] = { 0.0, 0.0, 0.0 };
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+      u[v] = U[o + g.sv * v];
+    if constexpr (GRAV) {
+#pragma unroll
+      for (int cc = 0; cc < DIM; ++cc)
+        gv[cc] = grav[o + g.sv * cc];
+    }
+    m = dmax(m, hydro_cell_invdt<DIM, GRAV>(g, u, gv));
+  }
+  __shared__ double red[8];
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0)
+    red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double r = (threadIdx.x < 8) ? red[threadIdx.x] : 0.0;
+    r = warp_max(r);
+    if (threadIdx.x == 0)
+      atomic_max_nonneg(out_bits, r);
+  }
+}
+
+} // namespace ek

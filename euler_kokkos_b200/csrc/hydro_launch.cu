@@ -1,0 +1,117 @@
+// Host-side dispatch of the fused hydro step: picks the template instance (dimension, Riemann
+// solver, gravity) and sizes the grid for the 148 SMs of a B200.
+#include "ek_internal.h"
+#include "hydro_kernels.cuh"
+
+namespace ek {
+
+#ifndef EK_HYDRO_TY
+#define EK_HYDRO_TY 12 // interior rows per tile: TY+4 warps per CTA
+#endif
+constexpr int TY = EK_HYDRO_TY;
+
+// z-chunk length: enough CTAs to fill whole waves over the SMs, long enough to amortise the
+// 3-plane pipeline warm-up of every chunk.
+static int pick_zchunk(int nz, long long xy_ctas, int sm_count)
+{
+  int best = nz;
+  double best_cost = 1e300;
+  for (int nchunk = 1; nchunk <= nz; ++nchunk) {
+    const int zc = (nz + nchunk - 1) / nchunk;
+    if (zc < 8 && nchunk > 1)
+      break;
+    const long long real_chunks = (nz + zc - 1) / zc;
+    const long long ctas = xy_ctas * real_chunks;
+    const long long waves = (ctas + sm_count - 1) / sm_count;
+    const double tail = (double)(waves * sm_count) / (double)ctas; // idle-SM factor of the last wave
+    const double warm = (double)(zc + 2.5) / (double)zc;           // pipeline warm-up per chunk
+    const double cost = tail * warm;
+    if (cost < best_cost - 1e-12) {
+      best_cost = cost;
+      best = zc;
+    }
+  }
+  return best;
+}
+
+template <int DIM, int RS, bool GRAV>
+static cudaError_t launch_one(Ctx& c, const double* Uin, double* Uout)
+{
+  using Smem = HydroSmem<DIM, TY>;
+  auto kern = hydro_step_kernel<DIM, RS, TY, GRAV>;
+  static bool attr_done[16] = { false };
+  const size_t smem = sizeof(Smem);
+  if (!attr_done[c.device & 15]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess)
+      return e;
+    attr_done[c.device & 15] = true;
+  }
+  HydroArgs a;
+  a.g = c.g;
+  a.Uin = Uin;
+  a.Uout = Uout;
+  a.grav = c.grav;
+  a.ts = c.ts;
+  dim3 block(32, TY + 4, 1);
+  dim3 grid((c.g.nx + HTX - 1) / HTX, (c.g.ny + TY - 1) / TY, 1);
+  a.zchunk = 1;
+  if (DIM == 3) {
+    a.zchunk = pick_zchunk(c.g.nz, (long long)grid.x * grid.y, c.sm_count);
+    grid.z = (c.g.nz + a.zchunk - 1) / a.zchunk;
+  }
+  kern<<<grid, block, smem, c.stream>>>(a);
+  c.launches++;
+  return cudaGetLastError();
+}
+
+template <int DIM, int RS>
+static cudaError_t launch_grav(Ctx& c, const double* Uin, double* Uout)
+{
+  if (c.p.gravity_enabled)
+    return launch_one<DIM, RS, true>(c, Uin, Uout);
+  return launch_one<DIM, RS, false>(c, Uin, Uout);
+}
+
+cudaError_t launch_hydro_step(Ctx& c, const double* Uin, double* Uout)
+{
+  if (c.p.dim == 3) {
+    switch (c.p.riemann) {
+      case RIEMANN_HLLC: return launch_grav<3, RIEMANN_HLLC>(c, Uin, Uout);
+      case RIEMANN_APPROX: return launch_grav<3, RIEMANN_APPROX>(c, Uin, Uout);
+      case RIEMANN_LLF: return launch_grav<3, RIEMANN_LLF>(c, Uin, Uout);
+      default: return cudaErrorInvalidValue;
+    }
+  }
+  switch (c.p.riemann) {
+    case RIEMANN_HLLC: return launch_grav<2, RIEMANN_HLLC>(c, Uin, Uout);
+    case RIEMANN_APPROX: return launch_grav<2, RIEMANN_APPROX>(c, Uin, Uout);
+    case RIEMANN_LLF: return launch_grav<2, RIEMANN_LLF>(c, Uin, Uout);
+    case RIEMANN_HLL: return launch_grav<2, RIEMANN_HLL>(c, Uin, Uout);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+cudaError_t launch_hydro_invdt(Ctx& c, const double* U)
+{
+  const long long ncell = (long long)c.g.nx * c.g.ny * c.g.nz;
+  long long nb = (ncell + 255) / 256;
+  if (nb > (long long)c.sm_count * 8)
+    nb = (long long)c.sm_count * 8;
+  const bool grav = c.p.gravity_enabled != 0;
+  if (c.p.dim == 3) {
+    if (grav)
+      hydro_invdt_kernel<3, true><<<(int)nb, 256, 0, c.stream>>>(c.g, U, c.grav, &c.ts->invdt_bits);
+    else
+      hydro_invdt_kernel<3, false><<<(int)nb, 256, 0, c.stream>>>(c.g, U, c.grav, &c.ts->invdt_bits);
+  } else {
+    if (grav)
+      hydro_invdt_kernel<2, true><<<(int)nb, 256, 0, c.stream>>>(c.g, U, c.grav, &c.ts->invdt_bits);
+    else
+      hydro_invdt_kernel<2, false><<<(int)nb, 256, 0, c.stream>>>(c.g, U, c.grav, &c.ts->invdt_bits);
+  }
+  c.launches++;
+  return cudaGetLastError();
+}
+
+} // namespace ek

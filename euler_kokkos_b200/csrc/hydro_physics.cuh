@@ -1,0 +1,334 @@
+// Euler (hydro) per-cell / per-face device functions, FP64, restructured for instruction count:
+// one reciprocal per cell in cons->prim and trace, shared reciprocals in the Riemann solvers,
+// the Riemann solver selected at compile time.
+//
+// Semantics follow the reference (citations relative to /root/reference/src):
+//   computePrimitives                      muscl/HydroBaseFunctor3D.h:81-107, HydroBaseFunctor2D.h:81-105
+//   slope_unsplit_hydro_{2d,3d}_scalar     muscl/HydroBaseFunctor3D.h:413-461
+//   trace_unsplit_{2d,3d}_along_dir        muscl/HydroBaseFunctor3D.h:276-389, HydroBaseFunctor2D.h:218-286
+//   riemann_approx/llf/hll/hllc, cmpflx    shared/RiemannSolvers.h:21-568
+#pragma once
+#include "ek_common.cuh"
+
+namespace ek {
+
+template <int DIM>
+struct HydroTraits {
+  static constexpr int NV = (DIM == 3) ? 5 : 4;
+};
+
+// ---- conservative -> primitive ---------------------------------------------------------------
+template <int DIM>
+__device__ __forceinline__ void hydro_cons_to_prim(const Grid& g, const double* __restrict__ u, double* __restrict__ q,
+                                                   double& rd_out)
+{
+  const double d = dmax(u[ID], g.smallr);
+  const double rd = rcp_fast(d);
+  const double ux = u[IU] * rd;
+  const double uy = u[IV] * rd;
+  double eken;
+  if constexpr (DIM == 3) {
+    const double uz = u[IW] * rd;
+    eken = 0.5 * (ux * ux + uy * uy + uz * uz);
+    q[IW] = uz;
+  } else {
+    eken = 0.5 * (ux * ux + uy * uy);
+  }
+  const double e = u[IP] * rd - eken;
+  q[ID] = d;
+  q[IP] = dmax((g.gamma0 - 1.0) * d * e, d * g.smallp);
+  q[IU] = ux;
+  q[IV] = uy;
+  rd_out = rd;
+}
+
+// inverse-dt contribution of one cell (ComputeDtFunctor{2D,3D}, HydroRunFunctors3D.h:44-82;
+// ComputeDtGravityFunctor{2D,3D}, :133-189)
+template <int DIM, bool GRAV>
+__device__ __forceinline__ double hydro_cell_invdt(const Grid& g, const double* __restrict__ u, const double* __restrict__ gvec)
+{
+  double q[5], rd;
+  hydro_cons_to_prim<DIM>(g, u, q, rd);
+  const double c = sqrt(g.gamma0 * q[IP] * rd);
+  if constexpr (!GRAV) {
+    double s = (c + fabs(q[IU])) / g.dx + (c + fabs(q[IV])) / g.dy;
+    if constexpr (DIM == 3)
+      s += (c + fabs(q[IW])) / g.dz;
+    return s;
+  } else {
+    double dxm = dmin(g.dx, g.dy);
+    if constexpr (DIM == 3)
+      dxm = dmin(dxm, g.dz);
+    double vel = (c + fabs(q[IU])) + (c + fabs(q[IV]));
+    double kk = fabs(gvec[0]) + fabs(gvec[1]);
+    if constexpr (DIM == 3) {
+      vel += c + fabs(q[IW]);
+      kk += fabs(gvec[2]);
+    }
+    kk *= g.cfl * dxm / (vel * vel);
+    kk = dmax(kk, 1e-4);
+    vel *= kk / (sqrt(1.0 + 2.0 * kk) - 1.0);
+    return vel / dxm;
+  }
+}
+
+// ---- limited slope ---------------------------------------------------------------------------
+__device__ __forceinline__ double limited_slope(double st, double qm, double q, double qp)
+{
+  const double dl = st * (q - qm);
+  const double dr = st * (qp - q);
+  const double dc = 0.5 * (qp - qm);
+  double lim = dmin(fabs(dl), fabs(dr));
+  lim = (dl * dr <= 0.0) ? 0.0 : lim;
+  const double m = dmin(lim, fabs(dc));
+  return (dc >= 0.0) ? m : -m;
+}
+
+// ---- Hancock predictor: source terms of one cell ---------------------------------------------
+// s[v] = time derivative of primitive variable v (to be multiplied by dt/dx_d * 0.5 per face)
+template <int DIM>
+__device__ __forceinline__ void hydro_sources(const Grid& g, const double* __restrict__ q, const double (*dq)[5], double* __restrict__ s)
+{
+  const double r = q[ID], p = q[IP], u = q[IU], v = q[IV];
+  const double rr = rcp_fast(r);
+  if constexpr (DIM == 3) {
+    const double w = q[IW];
+    const double div = dq[0][IU] + dq[1][IV] + dq[2][IW];
+    s[ID] = -u * dq[0][ID] - v * dq[1][ID] - w * dq[2][ID] - div * r;
+    s[IP] = -u * dq[0][IP] - v * dq[1][IP] - w * dq[2][IP] - div * g.gamma0 * p;
+    s[IU] = -u * dq[0][IU] - v * dq[1][IU] - w * dq[2][IU] - dq[0][IP] * rr;
+    s[IV] = -u * dq[0][IV] - v * dq[1][IV] - w * dq[2][IV] - dq[1][IP] * rr;
+    s[IW] = -u * dq[0][IW] - v * dq[1][IW] - w * dq[2][IW] - dq[2][IP] * rr;
+  } else {
+    const double div = dq[0][IU] + dq[1][IV];
+    s[ID] = -u * dq[0][ID] - v * dq[1][ID] - div * r;
+    s[IP] = -u * dq[0][IP] - v * dq[1][IP] - div * g.gamma0 * p;
+    s[IU] = -u * dq[0][IU] - v * dq[1][IU] - dq[0][IP] * rr;
+    s[IV] = -u * dq[0][IV] - v * dq[1][IV] - dq[1][IP] * rr;
+  }
+}
+
+// ---- Riemann solvers: q = (rho, p, un, ut1[, ut2]) in the face-normal frame -------------------
+template <int DIM>
+__device__ __forceinline__ void riemann_hllc(const Grid& g, const double* __restrict__ ql, const double* __restrict__ qr, double* __restrict__ flux)
+{
+  const double entho = 1.0 / (g.gamma0 - 1.0);
+  const double rl = dmax(ql[ID], g.smallr);
+  const double pl = dmax(ql[IP], rl * g.smallp);
+  const double ul = ql[IU];
+  double ecinl = 0.5 * rl * ul * ul;
+  ecinl += 0.5 * rl * ql[IV] * ql[IV];
+  if constexpr (DIM == 3)
+    ecinl += 0.5 * rl * ql[IW] * ql[IW];
+  const double etotl = pl * entho + ecinl;
+
+  const double rr = dmax(qr[ID], g.smallr);
+  const double pr = dmax(qr[IP], rr * g.smallp);
+  const double ur = qr[IU];
+  double ecinr = 0.5 * rr * ur * ur;
+  ecinr += 0.5 * rr * qr[IV] * qr[IV];
+  if constexpr (DIM == 3)
+    ecinr += 0.5 * rr * qr[IW] * qr[IW];
+  const double etotr = pr * entho + ecinr;
+
+  const double sc2 = g.smallc * g.smallc;
+  const double cfastl = sqrt(dmax(div_fast(g.gamma0 * pl, rl), sc2));
+  const double cfastr = sqrt(dmax(div_fast(g.gamma0 * pr, rr), sc2));
+  const double cmax = dmax(cfastl, cfastr);
+  const double SL = dmin(ul, ur) - cmax;
+  const double SR = dmax(ul, ur) + cmax;
+
+  const double rcl = rl * (ul - SL);
+  const double rcr = rr * (SR - ur);
+  const double irc = rcp_fast(rcr + rcl);
+  const double ustar = (rcr * ur + rcl * ul + (pl - pr)) * irc;
+  const double pstar = (rcr * pl + rcl * pr + rcl * rcr * (ul - ur)) * irc;
+
+  // sample at x/t = 0: pick the side first, then evaluate only that star state
+  const bool left = (ustar > 0.0);
+  const double S = left ? SL : SR;
+  const double ro_ = left ? rl : rr;
+  const double uo_ = left ? ul : ur;
+  const double po_ = left ? pl : pr;
+  const double eo_ = left ? etotl : etotr;
+  const double is = rcp_fast(S - ustar);
+  const double rstar = ro_ * (S - uo_) * is;
+  const double estar = ((S - uo_) * eo_ - po_ * uo_ + pstar * ustar) * is;
+
+  double ro, uo, po, eo;
+  if (SL > 0.0) {
+    ro = rl; uo = ul; po = pl; eo = etotl;
+  } else if (ustar > 0.0) {
+    ro = rstar; uo = ustar; po = pstar; eo = estar;
+  } else if (SR > 0.0) {
+    ro = rstar; uo = ustar; po = pstar; eo = estar;
+  } else {
+    ro = rr; uo = ur; po = pr; eo = etotr;
+  }
+  const double fm = ro * uo;
+  flux[ID] = fm;
+  flux[IU] = fm * uo + po;
+  flux[IP] = (eo + po) * uo;
+  const bool up = fm > 0.0;
+  flux[IV] = fm * (up ? ql[IV] : qr[IV]);
+  if constexpr (DIM == 3)
+    flux[IW] = fm * (up ? ql[IW] : qr[IW]);
+}
+
+template <int DIM>
+__device__ __forceinline__ void hydro_cmpflx(const Grid& g, const double* __restrict__ qg, double* __restrict__ flux)
+{
+  const double fm = qg[ID] * qg[IU];
+  flux[ID] = fm;
+  flux[IU] = fm * qg[IU] + qg[IP];
+  flux[IV] = fm * qg[IV];
+  const double entho = 1.0 / (g.gamma0 - 1.0);
+  double ekin = 0.5 * qg[ID] * (qg[IU] * qg[IU] + qg[IV] * qg[IV]);
+  if constexpr (DIM == 3) {
+    flux[IW] = fm * qg[IW];
+    ekin += 0.5 * qg[ID] * (qg[IW] * qg[IW]);
+  }
+  const double etot = qg[IP] * entho + ekin;
+  flux[IP] = qg[IU] * (etot + qg[IP]);
+}
+
+template <int DIM>
+__device__ __forceinline__ void riemann_approx(const Grid& g, const double* __restrict__ ql, const double* __restrict__ qr, double* __restrict__ flux)
+{
+  const double gamma0 = g.gamma0, gamma6 = g.gamma6;
+  const double rl = dmax(ql[ID], g.smallr), ul = ql[IU], pl = dmax(ql[IP], rl * g.smallp);
+  const double rr = dmax(qr[ID], g.smallr), ur = qr[IU], pr = dmax(qr[IP], rr * g.smallp);
+  const double cl = gamma0 * pl * rl;
+  const double cr = gamma0 * pr * rr;
+  double wl = sqrt(cl);
+  double wr = sqrt(cr);
+  double pstar = dmax(((wr * pl + wl * pr) + wl * wr * (ul - ur)) / (wl + wr), 0.0);
+  double pold = pstar;
+  double conv = 1.0;
+  const double ipl = 1.0 / pl, ipr = 1.0 / pr;
+  // Newton-Raphson, at most 10 iterations (the ini's niter_riemann is ignored by the reference,
+  // shared/RiemannSolvers.h:94)
+  for (int iter = 0; (iter < 10) && (conv > 1e-6); ++iter) {
+    const double wwl = sqrt(cl * (1.0 + gamma6 * (pold - pl) * ipl));
+    const double wwr = sqrt(cr * (1.0 + gamma6 * (pold - pr) * ipr));
+    const double ql_ = 2.0 * wwl * wwl * wwl / (wwl * wwl + cl);
+    const double qr_ = 2.0 * wwr * wwr * wwr / (wwr * wwr + cr);
+    const double usl = ul - (pold - pl) / wwl;
+    const double usr = ur + (pold - pr) / wwr;
+    const double delp = dmax(qr_ * ql_ / (qr_ + ql_) * (usl - usr), -pold);
+    pold = pold + delp;
+    conv = fabs(delp / (pold + g.smallpp));
+  }
+  pstar = pold;
+  wl = sqrt(cl * (1.0 + gamma6 * (pstar - pl) * ipl));
+  wr = sqrt(cr * (1.0 + gamma6 * (pstar - pr) * ipr));
+  const double ustar = 0.5 * (ul + (pl - pstar) / wl + ur - (pr - pstar) / wr);
+  const double sgnm = copysign(1.0, ustar);
+  const bool left = sgnm > 0.0;
+  const double ro = left ? rl : rr, uo = left ? ul : ur, po = left ? pl : pr, wo = left ? wl : wr;
+  const double co = dmax(g.smallc, sqrt(fabs(gamma0 * po / ro)));
+  const double rstar = dmax(ro / (1.0 + ro * (po - pstar) / (wo * wo)), g.smallr);
+  const double cstar = dmax(g.smallc, sqrt(fabs(gamma0 * pstar / rstar)));
+  double spout = co - sgnm * uo;
+  double spin = cstar - sgnm * ustar;
+  const double ushock = wo / ro - sgnm * uo;
+  if (pstar >= po) {
+    spin = ushock;
+    spout = ushock;
+  }
+  const double scr = dmax(spout - spin, g.smallc + fabs(spout + spin));
+  double frac = 0.5 * (1.0 + (spout + spin) / scr);
+  if (frac != frac)
+    frac = 0.0;
+  else
+    frac = frac >= 1.0 ? 1.0 : frac <= 0.0 ? 0.0 : frac;
+  double qg[5];
+  qg[ID] = frac * rstar + (1.0 - frac) * ro;
+  qg[IU] = frac * ustar + (1.0 - frac) * uo;
+  qg[IP] = frac * pstar + (1.0 - frac) * po;
+  if (spout < 0.0) {
+    qg[ID] = ro; qg[IU] = uo; qg[IP] = po;
+  }
+  if (spin > 0.0) {
+    qg[ID] = rstar; qg[IU] = ustar; qg[IP] = pstar;
+  }
+  qg[IV] = left ? ql[IV] : qr[IV];
+  if constexpr (DIM == 3)
+    qg[IW] = left ? ql[IW] : qr[IW];
+  hydro_cmpflx<DIM>(g, qg, flux);
+}
+
+// conservative state + physical flux of one side (LLF / HLL)
+template <int DIM, bool HLL>
+__device__ __forceinline__ void hydro_cons_flux(const double* __restrict__ q, double entho, double* __restrict__ u, double* __restrict__ f)
+{
+  u[ID] = q[ID];
+  double e = q[IP] * entho + 0.5 * q[ID] * q[IU] * q[IU];
+  e += 0.5 * q[ID] * q[IV] * q[IV];
+  if constexpr (DIM == 3)
+    e += 0.5 * q[ID] * q[IW] * q[IW];
+  u[IP] = e;
+  u[IU] = q[ID] * q[IU];
+  u[IV] = q[ID] * q[IV];
+  f[ID] = HLL ? u[IU] : u[ID] * q[IU];
+  f[IP] = q[IU] * (u[IP] + q[IP]);
+  f[IU] = q[IP] + u[IU] * q[IU];
+  f[IV] = f[ID] * q[IV];
+  if constexpr (DIM == 3) {
+    u[IW] = q[ID] * q[IW];
+    f[IW] = f[ID] * q[IW];
+  }
+}
+
+template <int DIM>
+__device__ __forceinline__ void riemann_llf(const Grid& g, const double* __restrict__ ql, const double* __restrict__ qr, double* __restrict__ flux)
+{
+  constexpr int NV = HydroTraits<DIM>::NV;
+  const double entho = 1.0 / (g.gamma0 - 1.0);
+  const double rl = dmax(ql[ID], g.smallr), ul = ql[IU], pl = dmax(ql[IP], rl * g.smallp);
+  const double rr = dmax(qr[ID], g.smallr), ur = qr[IU], pr = dmax(qr[IP], rr * g.smallp);
+  const double cl = sqrt(g.gamma0 * pl / rl);
+  const double cr = sqrt(g.gamma0 * pr / rr);
+  const double cmax = dmax(fabs(ul) + cl, fabs(ur) + cr);
+  double uL[5], uR[5], fL[5], fR[5];
+  hydro_cons_flux<DIM, false>(ql, entho, uL, fL);
+  hydro_cons_flux<DIM, false>(qr, entho, uR, fR);
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+    flux[v] = 0.5 * (fL[v] + fR[v] - cmax * (uR[v] - uL[v]));
+}
+
+template <int DIM>
+__device__ __forceinline__ void riemann_hll(const Grid& g, const double* __restrict__ ql, const double* __restrict__ qr, double* __restrict__ flux)
+{
+  constexpr int NV = HydroTraits<DIM>::NV;
+  const double entho = 1.0 / (g.gamma0 - 1.0);
+  const double rl = dmax(ql[ID], g.smallr), ul = ql[IU], pl = dmax(ql[IP], rl * g.smallp);
+  const double rr = dmax(qr[ID], g.smallr), ur = qr[IU], pr = dmax(qr[IP], rr * g.smallp);
+  const double cl = sqrt(g.gamma0 * pl / rl);
+  const double cr = sqrt(g.gamma0 * pr / rr);
+  const double SL = dmin(dmin(ul, ur) - dmax(cl, cr), 0.0);
+  const double SR = dmax(dmax(ul, ur) + dmax(cl, cr), 0.0);
+  double uL[5], uR[5], fL[5], fR[5];
+  hydro_cons_flux<DIM, true>(ql, entho, uL, fL);
+  hydro_cons_flux<DIM, true>(qr, entho, uR, fR);
+  const double inv = 1.0 / (SR - SL);
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+    flux[v] = (SR * fL[v] - SL * fR[v] + SR * SL * (uR[v] - uL[v])) * inv;
+}
+
+template <int DIM, int RS>
+__device__ __forceinline__ void riemann_hydro(const Grid& g, const double* __restrict__ ql, const double* __restrict__ qr, double* __restrict__ flux)
+{
+  if constexpr (RS == RIEMANN_HLLC)
+    riemann_hllc<DIM>(g, ql, qr, flux);
+  else if constexpr (RS == RIEMANN_APPROX)
+    riemann_approx<DIM>(g, ql, qr, flux);
+  else if constexpr (RS == RIEMANN_LLF)
+    riemann_llf<DIM>(g, ql, qr, flux);
+  else
+    riemann_hll<DIM>(g, ql, qr, flux);
+}
+
+} // namespace ek
