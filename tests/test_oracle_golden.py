@@ -1,0 +1,73 @@
+"""CPU tests: the plain-C oracle (oracle/*.c) against the golden fixtures produced by the UNMODIFIED
+reference binary (tests/golden/make_golden.py), and the host layer's initial conditions against the
+reference's own.  These pin the oracle that the GPU parity tests use as checker."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from tests import util
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz"))
+
+# The oracle follows the reference's floating-point order; observed agreement is bit-exact or within
+# a few ulp (the reference is compiled -O3 without FMA, like the oracle).  Gate: 1e-13 relative L-inf
+# per physical group, i.e. 10x tighter than the 1e-12 gate of the GPU path.
+TOL = 1e-13
+
+
+def load_case(name):
+    from euler_kokkos_b200 import hostapi
+
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    with tempfile.NamedTemporaryFile("w", suffix=".ini", delete=False) as f:
+        f.write(str(z["ini"]))
+        path = f.name
+    try:
+        case = hostapi.Case(path)
+    finally:
+        os.unlink(path)
+    return z, case
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_initial_condition_matches_reference(name):
+    """Init*Functor restatements of the host layer (csrc/host/InitConditions.cpp) vs the reference's dump 0."""
+    from euler_kokkos_b200.vti import interior_of
+
+    z, case = load_case(name)
+    p = case.params
+    if name.startswith("mhdblast"):
+        pytest.skip("reference's MHD blast reads uninitialised [blast] bz values (BlastParams.h:56-62): no reproducible IC")
+    U, _ = case.new_state()
+    ours = interior_of(U, p.ghost, p.dim)
+    ref = z["u0"]
+    assert ours.shape == ref.shape
+    den = np.abs(ref).max()
+    assert np.abs(ours - ref).max() <= 1e-15 * den, np.abs(ours - ref).max()
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_free_run_matches_reference(name):
+    """N free-running steps of the oracle (its own dt) from the reference's initial dump."""
+    from euler_kokkos_b200.vti import embed_interior
+    from oracle import oracle_lib as O
+
+    z, case = load_case(name)
+    p = case.params
+    op = O.params_from(p)
+    grav = None
+    if p.gravity_enabled:
+        _, grav = case.new_state()
+    U = np.ascontiguousarray(embed_interior(z["u0"], p.ghost, p.dim))
+    if not p.mhd:
+        O.make_boundaries(op, U)
+    t, done = 0.0, 0
+    for s in [int(x) for x in z["steps"]]:
+        U, t, _ = O.run(op, U, s - done, t=t, grav=grav)
+        done = s
+        ref = np.ascontiguousarray(embed_interior(z[f"u{s}"], p.ghost, p.dim))
+        err = util.group_rel_linf(U, ref, p)
+        assert max(err.values()) < TOL, (name, s, err)
