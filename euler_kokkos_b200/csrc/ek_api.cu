@@ -5,6 +5,7 @@
 #include <cstring>
 #include <new>
 #include "ek_internal.h"
+#include "ek_grid.h"
 #include "boundary_kernels.cuh"
 
 using namespace ek;
@@ -131,27 +132,6 @@ static int validate(const ek_params& p, std::string& err)
   return EK_OK;
 }
 
-static Grid make_grid(const ek_params& p)
-{
-  Grid g{};
-  g.nx = p.nx; g.ny = p.ny; g.nz = (p.dim == 3) ? p.nz : 1;
-  g.gw = p.ghost;
-  g.isize = p.nx + 2 * p.ghost;
-  g.jsize = p.ny + 2 * p.ghost;
-  g.ksize = (p.dim == 3) ? p.nz + 2 * p.ghost : 1;
-  g.nbvar = p.nbvar;
-  g.sj = g.isize;
-  g.sk = (long long)g.isize * g.jsize;
-  g.sv = g.sk * g.ksize;
-  g.dx = p.dx; g.dy = p.dy; g.dz = p.dz;
-  g.gamma0 = p.gamma0; g.gamma6 = p.gamma6; g.smallr = p.smallr; g.smallc = p.smallc;
-  g.smallp = p.smallp; g.smallpp = p.smallpp; g.cfl = p.cfl; g.slope_type = p.slope_type;
-  for (int f = 0; f < 6; ++f) g.bc[f] = p.bc[f];
-  g.impl_version = p.impl_version;
-  g.gravity_hancock = p.gravity_enabled && p.gravity_hancock;
-  return g;
-}
-
 static int blocks_for(long long n, int sm_count)
 {
   long long b = (n + 255) / 256;
@@ -218,6 +198,7 @@ static int enqueue_step(Ctx& c, int use_host_dt, double host_dt, int max_steps)
     if (rc != EK_OK)
       return rc;
     if (!use_host_dt) {
+      EK_CUDA(&c, cudaMemsetAsync(&c.ts->invdt_bits, 0, sizeof(unsigned long long), c.stream));
       EK_CUDA(&c, launch_mhd_invdt(c, Uin));
       rc = comm_allreduce_invdt(c);
       if (rc != EK_OK)
@@ -377,6 +358,7 @@ int ek_upload_state(ek_ctx* ctx, const double* U_host)
   EK_CUDA(c, cudaMemcpyAsync(c->U[0], U_host, bytes, cudaMemcpyHostToDevice, c->stream));
   EK_CUDA(c, cudaMemcpyAsync(c->U[1], c->U[0], bytes, cudaMemcpyDeviceToDevice, c->stream));
   c->dt_primed = false;
+  c->mhd_prims_of = nullptr;
   EK_CUDA(c, cudaStreamSynchronize(c->stream)); // the host buffer may be pageable / reused
   return EK_OK;
 }
@@ -397,6 +379,7 @@ int ek_device_state(ek_ctx* ctx, double** dptr)
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
   *dptr = c->U[c->cur];
   c->dt_primed = false; // the caller may modify the state through this pointer
+  c->mhd_prims_of = nullptr;
   return EK_OK;
 }
 

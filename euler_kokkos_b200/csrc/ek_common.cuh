@@ -1,6 +1,13 @@
 // Shared device-side definitions for the B200 MUSCL-Hancock kernels (sm_100a, FP64).
 #pragma once
+#ifdef __CUDACC__
 #include <cuda_runtime.h>
+#define EK_HD __host__ __device__ __forceinline__
+#else
+// host-only inclusion (tests/emul: the per-cell device functions compiled by g++ for CPU-side checks)
+#include <cmath>
+#define EK_HD inline
+#endif
 #include <stdint.h>
 
 namespace ek {
@@ -33,8 +40,8 @@ struct Grid {
   int gravity_hancock;
 };
 
-__device__ __forceinline__ double dmax(double a, double b) { return fmax(a, b); }
-__device__ __forceinline__ double dmin(double a, double b) { return fmin(a, b); }
+EK_HD double dmax(double a, double b) { return fmax(a, b); }
+EK_HD double dmin(double a, double b) { return fmin(a, b); }
 
 // ---------------------------------------------------------------------------------------------
 // Division / square root.  EK_PRECISE_MATH=1 uses IEEE-rounded '/' and sqrt() everywhere (parity
@@ -46,9 +53,9 @@ __device__ __forceinline__ double dmin(double a, double b) { return fmin(a, b); 
 #define EK_PRECISE_MATH 0
 #endif
 
-__device__ __forceinline__ double rcp_fast(double x)
+EK_HD double rcp_fast(double x)
 {
-#if EK_PRECISE_MATH
+#if EK_PRECISE_MATH || !defined(__CUDA_ARCH__)
   return 1.0 / x;
 #else
   double y;
@@ -61,9 +68,9 @@ __device__ __forceinline__ double rcp_fast(double x)
 #endif
 }
 
-__device__ __forceinline__ double div_fast(double a, double b)
+EK_HD double div_fast(double a, double b)
 {
-#if EK_PRECISE_MATH
+#if EK_PRECISE_MATH || !defined(__CUDA_ARCH__)
   return a / b;
 #else
   double y = rcp_fast(b);
@@ -74,15 +81,28 @@ __device__ __forceinline__ double div_fast(double a, double b)
 }
 
 // sqrt for x >= 0 (x == 0 handled)
-__device__ __forceinline__ double sqrt_fast(double x)
+EK_HD double sqrt_fast(double x)
 {
-#if EK_PRECISE_MATH
-  return sqrt(x);
-#else
   return sqrt(x); // nvcc's FP64 sqrt is already MUFU.RSQ64H + Newton; kept IEEE for the floors
+}
+
+// 1/sqrt(x) for finite normal x > 0: MUFU.RSQ64H seed (rel. error 2^-22.9) + two Newton steps
+EK_HD double rsqrt_fast(double x)
+{
+#if EK_PRECISE_MATH || !defined(__CUDA_ARCH__)
+  return 1.0 / sqrt(x);
+#else
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x * y, y, 1.0);
+  y = fma(y, 0.5 * e, y);
+  e = fma(-x * y, y, 1.0);
+  y = fma(y, 0.5 * e, y);
+  return y;
 #endif
 }
 
+#ifdef __CUDACC__
 // order-preserving atomic max for non-negative doubles
 __device__ __forceinline__ void atomic_max_nonneg(unsigned long long* addr, double v)
 {
@@ -96,5 +116,7 @@ __device__ __forceinline__ double warp_max(double v)
     v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
+
+#endif // __CUDACC__
 
 } // namespace ek

@@ -29,6 +29,7 @@ struct Ctx {
   int64_t state_len = 0;
   int64_t launches = 0;
   bool dt_primed = false; // ts->invdt_bits holds max invDt of the current level
+  const double* mhd_prims_of = nullptr; // level whose primitives currently sit in the MHD work area
   int sm_count = 148;
   // communicator (z-slab / cartesian neighbours)
   void* nccl_comm = nullptr;

@@ -1,0 +1,107 @@
+// CUDA kernels of the CT-MHD step: thin thread->cell mappings over the per-cell stages of
+// mhd_cells.cuh.  One thread per cell of the ghosted box, flattened index (i fastest => coalesced,
+// no partially filled blocks along x for sizes like 518).
+#pragma once
+#include "mhd_cells.cuh"
+
+namespace ek {
+
+struct MhdArgs {
+  Grid g;
+  const double* __restrict__ Uin;
+  double* __restrict__ Uout;
+  double* __restrict__ work;
+  TimeState* ts;
+};
+
+__device__ __forceinline__ bool mhd_cell_of_thread(const Grid& g, int& i, int& j, int& k)
+{
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= g.sv)
+    return false;
+  k = (int)(c / g.sk);
+  const int r = (int)(c - (long long)k * g.sk);
+  j = r / g.isize;
+  i = r - j * g.isize;
+  return true;
+}
+
+// stage P + CFL max-reduction (warp shuffles, then one atomic per CTA: grid reduce)
+__global__ void __launch_bounds__(256) mhd_prims_kernel(const MhdArgs a, const int do_invdt)
+{
+  if (a.ts->finished)
+    return;
+  const MhdWork w = mhd_work_split(a.work, a.g.sv);
+  int i, j, k;
+  double m = 0.0;
+  if (mhd_cell_of_thread(a.g, i, j, k))
+    m = mhd_stage_prims(a.g, a.Uin, w.Q, i, j, k);
+  if (!do_invdt)
+    return;
+  __shared__ double red[8];
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0)
+    red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double r = (threadIdx.x < 8) ? red[threadIdx.x] : 0.0;
+    r = warp_max(r);
+    if (threadIdx.x == 0 && r > 0.0)
+      atomic_max_nonneg(&a.ts->invdt_bits, r);
+  }
+}
+
+__global__ void __launch_bounds__(256) mhd_elec_kernel(const MhdArgs a)
+{
+  if (a.ts->finished)
+    return;
+  const MhdWork w = mhd_work_split(a.work, a.g.sv);
+  int i, j, k;
+  if (mhd_cell_of_thread(a.g, i, j, k))
+    mhd_stage_elec(a.g, a.Uin, w.Q, w.E, i, j, k);
+}
+
+__global__ void __launch_bounds__(256) mhd_trace_kernel(const MhdArgs a)
+{
+  if (a.ts->finished)
+    return;
+  const MhdWork w = mhd_work_split(a.work, a.g.sv);
+  const double dt = a.ts->dt;
+  int i, j, k;
+  if (mhd_cell_of_thread(a.g, i, j, k))
+    mhd_stage_trace(a.g, a.Uin, w.Q, w.E, w.S, dt / a.g.dx, dt / a.g.dy, dt / a.g.dz, i, j, k);
+}
+
+template <int RS>
+__global__ void __launch_bounds__(128) mhd_flux_kernel(const MhdArgs a)
+{
+  if (a.ts->finished)
+    return;
+  const MhdWork w = mhd_work_split(a.work, a.g.sv);
+  int i, j, k;
+  if (mhd_cell_of_thread(a.g, i, j, k))
+    mhd_stage_fluxes<RS>(a.g, w.S, w.F, i, j, k);
+}
+
+__global__ void __launch_bounds__(128) mhd_emf_kernel(const MhdArgs a)
+{
+  if (a.ts->finished)
+    return;
+  const MhdWork w = mhd_work_split(a.work, a.g.sv);
+  int i, j, k;
+  if (mhd_cell_of_thread(a.g, i, j, k))
+    mhd_stage_emfs(a.g, w.S, w.EMF, i, j, k);
+}
+
+__global__ void __launch_bounds__(256) mhd_update_kernel(const MhdArgs a)
+{
+  if (a.ts->finished)
+    return;
+  const MhdWork w = mhd_work_split(a.work, a.g.sv);
+  const double dt = a.ts->dt;
+  int i, j, k;
+  if (mhd_cell_of_thread(a.g, i, j, k))
+    mhd_stage_update(a.g, a.Uin, w.F, w.EMF, a.Uout, dt / a.g.dx, dt / a.g.dy, dt / a.g.dz, i, j, k);
+}
+
+} // namespace ek

@@ -1,0 +1,41 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes loader of the host build of the per-cell CUDA stages (mhd_emul.cpp)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        subprocess.run(["make", "-C", _HERE, "-s"], check=True)
+        _lib = C.CDLL(os.path.join(_HERE, "_build", "libek_emul.so"))
+        dp = C.POINTER(C.c_double)
+        _lib.emul_mhd_invdt.restype = C.c_double
+        _lib.emul_mhd_invdt.argtypes = [C.c_void_p, dp, dp]
+        _lib.emul_mhd_work_len.restype = C.c_longlong
+        _lib.emul_mhd_work_len.argtypes = [C.c_void_p]
+        _lib.emul_mhd_step.argtypes = [C.c_void_p, dp, dp, dp, C.c_double]
+    return _lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def mhd_invdt(p, U):
+    work = np.zeros(lib().emul_mhd_work_len(C.byref(p)))
+    return lib().emul_mhd_invdt(C.byref(p), _dp(U), _dp(work))
+
+
+def mhd_step(p, U, dt):
+    """U: ghost-filled state.  Returns the new state (ghosts copied from U)."""
+    work = np.zeros(lib().emul_mhd_work_len(C.byref(p)))
+    out = U.copy()
+    rc = lib().emul_mhd_step(C.byref(p), _dp(U), _dp(out), _dp(work), float(dt))
+    assert rc == 0
+    return out

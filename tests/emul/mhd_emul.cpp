@@ -1,0 +1,53 @@
+// TEST INFRASTRUCTURE ONLY: the per-cell stages of the CUDA MHD path (euler_kokkos_b200/csrc/
+// mhd_cells.cuh, mhd_physics.cuh -- the very functions the kernels call) compiled for the HOST and
+// driven by plain loops, so that the kernel logic can be checked against the oracle on a machine
+// without a GPU (pytest -m "not gpu").  Never loaded by the product library.
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../euler_kokkos_b200/csrc/ek_grid.h"
+#include "../../euler_kokkos_b200/csrc/mhd_cells.cuh"
+
+using namespace ek;
+
+template <int RS>
+static void step(const Grid& g, const double* Uin, double* Uout, double* work, double dt)
+{
+  const MhdWork w = mhd_work_split(work, g.sv);
+  const double dtdx = dt / g.dx, dtdy = dt / g.dy, dtdz = dt / g.dz;
+#define LOOP for (int k = 0; k < g.ksize; ++k) for (int j = 0; j < g.jsize; ++j) for (int i = 0; i < g.isize; ++i)
+  LOOP mhd_stage_elec(g, Uin, w.Q, w.E, i, j, k);
+  LOOP mhd_stage_trace(g, Uin, w.Q, w.E, w.S, dtdx, dtdy, dtdz, i, j, k);
+  LOOP mhd_stage_fluxes<RS>(g, w.S, w.F, i, j, k);
+  LOOP mhd_stage_emfs(g, w.S, w.EMF, i, j, k);
+  LOOP mhd_stage_update(g, Uin, w.F, w.EMF, Uout, dtdx, dtdy, dtdz, i, j, k);
+}
+
+extern "C" {
+
+// max inverse dt of a ghost-filled state (stage P); Q is left in `work`
+double emul_mhd_invdt(const ek_params* p, const double* U, double* work)
+{
+  const Grid g = make_grid(*p);
+  const MhdWork w = mhd_work_split(work, g.sv);
+  double m = 0.0;
+  LOOP m = fmax(m, mhd_stage_prims(g, U, w.Q, i, j, k));
+  return m;
+}
+
+long long emul_mhd_work_len(const ek_params* p) { return (long long)W_TOTAL * make_grid(*p).sv; }
+
+// one step with a given dt on a ghost-filled Uin; Uout must be a copy of Uin (ghosts are not written)
+int emul_mhd_step(const ek_params* p, const double* Uin, double* Uout, double* work, double dt)
+{
+  const Grid g = make_grid(*p);
+  emul_mhd_invdt(p, Uin, work);
+  switch (p->riemann) {
+    case RIEMANN_HLLD: step<RIEMANN_HLLD>(g, Uin, Uout, work, dt); return 0;
+    case RIEMANN_HLL: step<RIEMANN_HLL>(g, Uin, Uout, work, dt); return 0;
+    case RIEMANN_LLF: step<RIEMANN_LLF>(g, Uin, Uout, work, dt); return 0;
+  }
+  return 1;
+}
+}
