@@ -34,14 +34,18 @@ struct Grid {
   int nbvar;
   long long sj, sk, sv;    // strides (in doubles) of j, k, var
   double dx, dy, dz;
+  double invdx, invdy, invdz; // 1/dx, 1/dy, 1/dz (IEEE, computed on the host)
   double gamma0, gamma6, smallr, smallc, smallp, smallpp, cfl, slope_type;
+  double entho;               // 1/(gamma0-1)
   int bc[6];
   int impl_version;
   int gravity_hancock;
 };
 
-EK_HD double dmax(double a, double b) { return fmax(a, b); }
-EK_HD double dmin(double a, double b) { return fmin(a, b); }
+// max/min as compare+select (3 instructions; fmax/fmin expand to a 6-instruction NaN-aware sequence
+// on sm_100a).  NaN semantics differ from fmax/fmin only when an operand IS a NaN.
+EK_HD double dmax(double a, double b) { return (a > b) ? a : b; }
+EK_HD double dmin(double a, double b) { return (a < b) ? a : b; }
 
 // ---------------------------------------------------------------------------------------------
 // Division / square root.  EK_PRECISE_MATH=1 uses IEEE-rounded '/' and sqrt() everywhere (parity
@@ -80,10 +84,24 @@ EK_HD double div_fast(double a, double b)
 #endif
 }
 
-// sqrt for x >= 0 (x == 0 handled)
+// sqrt for x >= 0 (zero and subnormal inputs give 0): MUFU.RSQ64H seed, one Goldschmidt step and a
+// Newton correction (7 FP64 ops, error <= ~1 ulp), without the IEEE slow-path branch of sqrt()
 EK_HD double sqrt_fast(double x)
 {
-  return sqrt(x); // nvcc's FP64 sqrt is already MUFU.RSQ64H + Newton; kept IEEE for the floors
+#if EK_PRECISE_MATH || !defined(__CUDA_ARCH__)
+  return sqrt(x);
+#else
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double g = x * y;
+  double h = 0.5 * y;
+  const double r = fma(-h, g, 0.5);
+  g = fma(g, r, g);
+  h = fma(h, r, h);
+  const double d = fma(-g, g, x);
+  g = fma(d, h, g);
+  return (x >= 2.2250738585072014e-308) ? g : 0.0;
+#endif
 }
 
 // 1/sqrt(x) for finite normal x > 0: MUFU.RSQ64H seed (rel. error 2^-22.9) + two Newton steps

@@ -49,11 +49,11 @@ __device__ __forceinline__ double hydro_cell_invdt(const Grid& g, const double* 
 {
   double q[5], rd;
   hydro_cons_to_prim<DIM>(g, u, q, rd);
-  const double c = sqrt(g.gamma0 * q[IP] * rd);
+  const double c = sqrt_fast(g.gamma0 * q[IP] * rd);
   if constexpr (!GRAV) {
-    double s = (c + fabs(q[IU])) / g.dx + (c + fabs(q[IV])) / g.dy;
+    double s = (c + fabs(q[IU])) * g.invdx + (c + fabs(q[IV])) * g.invdy;
     if constexpr (DIM == 3)
-      s += (c + fabs(q[IW])) / g.dz;
+      s += (c + fabs(q[IW])) * g.invdz;
     return s;
   } else {
     double dxm = dmin(g.dx, g.dy);
@@ -112,7 +112,7 @@ __device__ __forceinline__ void hydro_sources(const Grid& g, const double* __res
 template <int DIM>
 __device__ __forceinline__ void riemann_hllc(const Grid& g, const double* __restrict__ ql, const double* __restrict__ qr, double* __restrict__ flux)
 {
-  const double entho = 1.0 / (g.gamma0 - 1.0);
+  const double entho = g.entho;
   const double rl = dmax(ql[ID], g.smallr);
   const double pl = dmax(ql[IP], rl * g.smallp);
   const double ul = ql[IU];
@@ -132,9 +132,8 @@ __device__ __forceinline__ void riemann_hllc(const Grid& g, const double* __rest
   const double etotr = pr * entho + ecinr;
 
   const double sc2 = g.smallc * g.smallc;
-  const double cfastl = sqrt(dmax(div_fast(g.gamma0 * pl, rl), sc2));
-  const double cfastr = sqrt(dmax(div_fast(g.gamma0 * pr, rr), sc2));
-  const double cmax = dmax(cfastl, cfastr);
+  // max(sqrt(x), sqrt(y)) == sqrt(max(x, y)): one square root per face
+  const double cmax = sqrt_fast(dmax(dmax(div_fast(g.gamma0 * pl, rl), div_fast(g.gamma0 * pr, rr)), sc2));
   const double SL = dmin(ul, ur) - cmax;
   const double SR = dmax(ul, ur) + cmax;
 
@@ -182,7 +181,7 @@ __device__ __forceinline__ void hydro_cmpflx(const Grid& g, const double* __rest
   flux[ID] = fm;
   flux[IU] = fm * qg[IU] + qg[IP];
   flux[IV] = fm * qg[IV];
-  const double entho = 1.0 / (g.gamma0 - 1.0);
+  const double entho = g.entho;
   double ekin = 0.5 * qg[ID] * (qg[IU] * qg[IU] + qg[IV] * qg[IV]);
   if constexpr (DIM == 3) {
     flux[IW] = fm * qg[IW];
@@ -284,7 +283,7 @@ template <int DIM>
 __device__ __forceinline__ void riemann_llf(const Grid& g, const double* __restrict__ ql, const double* __restrict__ qr, double* __restrict__ flux)
 {
   constexpr int NV = HydroTraits<DIM>::NV;
-  const double entho = 1.0 / (g.gamma0 - 1.0);
+  const double entho = g.entho;
   const double rl = dmax(ql[ID], g.smallr), ul = ql[IU], pl = dmax(ql[IP], rl * g.smallp);
   const double rr = dmax(qr[ID], g.smallr), ur = qr[IU], pr = dmax(qr[IP], rr * g.smallp);
   const double cl = sqrt(g.gamma0 * pl / rl);
@@ -302,7 +301,7 @@ template <int DIM>
 __device__ __forceinline__ void riemann_hll(const Grid& g, const double* __restrict__ ql, const double* __restrict__ qr, double* __restrict__ flux)
 {
   constexpr int NV = HydroTraits<DIM>::NV;
-  const double entho = 1.0 / (g.gamma0 - 1.0);
+  const double entho = g.entho;
   const double rl = dmax(ql[ID], g.smallr), ul = ql[IU], pl = dmax(ql[IP], rl * g.smallp);
   const double rr = dmax(qr[ID], g.smallr), ur = qr[IU], pr = dmax(qr[IP], rr * g.smallp);
   const double cl = sqrt(g.gamma0 * pl / rl);

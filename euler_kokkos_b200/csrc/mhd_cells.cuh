@@ -22,7 +22,18 @@
 
 namespace ek {
 
-// work-array layout, in units of one cell-array (g.sv doubles)
+// Work arrays are private to the library, so they use a tiled "AoSoA" layout instead of the ABI's
+// SoA: [tile = c/32][variable][lane = c%32] over the flattened ghosted cell index c.  A warp of 32
+// consecutive cells reads one 256-byte segment per variable (coalesced), and the variable offset is
+// a compile-time constant: one base address per neighbour cell, immediate offsets for everything else.
+template <int NV>
+EK_HD size_t tile_off(unsigned c)
+{
+  return (size_t)(c >> 5) * (unsigned)(NV * 32) + (c & 31u);
+}
+constexpr int TL = 32; // stride between variables inside a tile
+
+// work-array layout, in units of one padded cell-array (mhd_padded_cells doubles)
 enum : int {
   WQ = 0,         // primitives, 8
   WE = 8,         // edge electric field Ex,Ey,Ez at the lower edges, 3
@@ -50,35 +61,47 @@ struct MhdWork {
   double* EMF;
 };
 
+EK_HD long long mhd_padded_cells(long long sv) { return ((sv + 31) / 32) * 32; }
+
 EK_HD MhdWork mhd_work_split(double* base, long long sv)
 {
+  const long long T = mhd_padded_cells(sv);
   MhdWork w;
-  w.Q = base + (long long)WQ * sv;
-  w.E = base + (long long)WE * sv;
-  w.S = base + (long long)WS * sv;
-  w.F = base + (long long)WF * sv;
-  w.EMF = base + (long long)WEMF * sv;
+  w.Q = base + (long long)WQ * T;
+  w.E = base + (long long)WE * T;
+  w.S = base + (long long)WS * T;
+  w.F = base + (long long)WF * T;
+  w.EMF = base + (long long)WEMF * T;
   return w;
 }
+
+// Cell addressing: c = i + isize*(j + jsize*k) as unsigned (the ghosted box of one B200 always has
+// < 2^31 cells); neighbour strides in c: 1, sj = isize, sk = isize*jsize.
+struct MhdIdx {
+  unsigned c, sj, sk;
+  int i, j, k;
+};
 
 // ---- stage P ------------------------------------------------------------------------------------
 // Q(i,j,k) for 0 <= i < isize-1 (the last layer is never written, MHDRunFunctors3D.h:120-122);
 // returns the cell's inverse-dt contribution (0 outside the interior).
-EK_HD double mhd_stage_prims(const Grid& g, const double* __restrict__ U, double* __restrict__ Q, int i, int j, int k)
+EK_HD double mhd_stage_prims(const Grid& g, const double* __restrict__ U, double* __restrict__ Q, const MhdIdx& x)
 {
-  if (i >= g.isize - 1 || j >= g.jsize - 1 || k >= g.ksize - 1)
+  if (x.i >= g.isize - 1 || x.j >= g.jsize - 1 || x.k >= g.ksize - 1)
     return 0.0;
-  const long long o = i + g.sj * j + g.sk * k;
+  const double* __restrict__ Uc = U + x.c;
+  const long long sv = g.sv;
   double u[8], q[8];
 #pragma unroll
   for (int v = 0; v < 8; ++v)
-    u[v] = U[o + g.sv * v];
-  mhd_cons_to_prim(g, u, U[o + 1 + g.sv * IA], U[o + g.sj + g.sv * IB], U[o + g.sk + g.sv * IC], q);
+    u[v] = Uc[sv * v];
+  mhd_cons_to_prim(g, u, Uc[sv * IA + 1], Uc[sv * IB + x.sj], Uc[sv * IC + x.sk], q);
+  double* __restrict__ Qc = Q + tile_off<8>(x.c);
 #pragma unroll
   for (int v = 0; v < 8; ++v)
-    Q[o + g.sv * v] = q[v];
+    Qc[TL * v] = q[v];
   const int gw = g.gw;
-  if (i >= gw && i < g.isize - gw && j >= gw && j < g.jsize - gw && k >= gw && k < g.ksize - gw)
+  if (x.i >= gw && x.i < g.isize - gw && x.j >= gw && x.j < g.jsize - gw && x.k >= gw && x.k < g.ksize - gw)
     return mhd_cell_invdt(g, q);
   return 0.0;
 }
@@ -86,73 +109,84 @@ EK_HD double mhd_stage_prims(const Grid& g, const double* __restrict__ U, double
 // ---- stage E ------------------------------------------------------------------------------------
 // E at the three lower edges of cell (i,j,k), 1 <= i <= isize-2 (MHDRunFunctors3D.h:303-352)
 EK_HD void mhd_stage_elec(const Grid& g, const double* __restrict__ U, const double* __restrict__ Q, double* __restrict__ E,
-                          int i, int j, int k)
+                          const MhdIdx& x)
 {
-  if (i < 1 || j < 1 || k < 1 || i > g.isize - 2 || j > g.jsize - 2 || k > g.ksize - 2)
+  if (x.i < 1 || x.j < 1 || x.k < 1 || x.i > g.isize - 2 || x.j > g.jsize - 2 || x.k > g.ksize - 2)
     return;
-  const long long o = i + g.sj * j + g.sk * k, sj = g.sj, sk = g.sk, sv = g.sv;
-  const double* __restrict__ Qu = Q + sv * IU;
-  const double* __restrict__ Qv = Q + sv * IV;
-  const double* __restrict__ Qw = Q + sv * IW;
-  const double* __restrict__ UA = U + sv * IA;
-  const double* __restrict__ UB = U + sv * IB;
-  const double* __restrict__ UC = U + sv * IC;
+  const unsigned c = x.c, sj = x.sj, sk = x.sk;
+  const long long sv = g.sv;
+  // velocities of the 7 cells touching the three lower edges
+  const double* __restrict__ q000 = Q + tile_off<8>(c);
+  const double* __restrict__ q100 = Q + tile_off<8>(c - 1);
+  const double* __restrict__ q010 = Q + tile_off<8>(c - sj);
+  const double* __restrict__ q001 = Q + tile_off<8>(c - sk);
+  const double* __restrict__ q110 = Q + tile_off<8>(c - 1 - sj);
+  const double* __restrict__ q101 = Q + tile_off<8>(c - 1 - sk);
+  const double* __restrict__ q011 = Q + tile_off<8>(c - sj - sk);
+  const double* __restrict__ UA = U + sv * IA + c;
+  const double* __restrict__ UB = U + sv * IB + c;
+  const double* __restrict__ UC = U + sv * IC + c;
+  const double A0 = UA[0], B0 = UB[0], C0 = UC[0];
   double u, v, w, A, B, C;
-  v = 0.25 * (Qv[o - sj - sk] + Qv[o - sj] + Qv[o - sk] + Qv[o]);
-  w = 0.25 * (Qw[o - sj - sk] + Qw[o - sj] + Qw[o - sk] + Qw[o]);
-  B = 0.5 * (UB[o - sk] + UB[o]);
-  C = 0.5 * (UC[o - sj] + UC[o]);
-  E[o] = v * C - w * B;
-  u = 0.25 * (Qu[o - 1 - sk] + Qu[o - 1] + Qu[o - sk] + Qu[o]);
-  w = 0.25 * (Qw[o - 1 - sk] + Qw[o - 1] + Qw[o - sk] + Qw[o]);
-  A = 0.5 * (UA[o - sk] + UA[o]);
-  C = 0.5 * (UC[o - 1] + UC[o]);
-  E[o + sv] = w * A - u * C;
-  u = 0.25 * (Qu[o - 1 - sj] + Qu[o - 1] + Qu[o - sj] + Qu[o]);
-  v = 0.25 * (Qv[o - 1 - sj] + Qv[o - 1] + Qv[o - sj] + Qv[o]);
-  A = 0.5 * (UA[o - sj] + UA[o]);
-  B = 0.5 * (UB[o - 1] + UB[o]);
-  E[o + 2 * sv] = u * B - v * A;
+  v = 0.25 * (q011[TL * IV] + q010[TL * IV] + q001[TL * IV] + q000[TL * IV]);
+  w = 0.25 * (q011[TL * IW] + q010[TL * IW] + q001[TL * IW] + q000[TL * IW]);
+  B = 0.5 * (UB[-(long long)sk] + B0);
+  C = 0.5 * (UC[-(long long)sj] + C0);
+  double* __restrict__ Ec = E + tile_off<3>(c);
+  Ec[0] = v * C - w * B;
+  u = 0.25 * (q101[TL * IU] + q100[TL * IU] + q001[TL * IU] + q000[TL * IU]);
+  w = 0.25 * (q101[TL * IW] + q100[TL * IW] + q001[TL * IW] + q000[TL * IW]);
+  A = 0.5 * (UA[-(long long)sk] + A0);
+  C = 0.5 * (UC[-1] + C0);
+  Ec[TL] = w * A - u * C;
+  u = 0.25 * (q110[TL * IU] + q100[TL * IU] + q010[TL * IU] + q000[TL * IU]);
+  v = 0.25 * (q110[TL * IV] + q100[TL * IV] + q010[TL * IV] + q000[TL * IV]);
+  A = 0.5 * (UA[-(long long)sj] + A0);
+  B = 0.5 * (UB[-1] + B0);
+  Ec[2 * TL] = u * B - v * A;
 }
 
 // ---- stage T ------------------------------------------------------------------------------------
 // Hancock predictor of cell (i,j,k) (trace_unsplit_mhd_3d_simpler, MHDBaseFunctor3D.h:690-914) and of
 // its three lower faces.  Cells in [2, isize-3], faces in [2, isize-2] (what stage R consumes).
 EK_HD void mhd_stage_trace(const Grid& g, const double* __restrict__ U, const double* __restrict__ Q, const double* __restrict__ E,
-                           double* __restrict__ S, double dtdx, double dtdy, double dtdz, int i, int j, int k)
+                           double* __restrict__ S, double dtdx, double dtdy, double dtdz, const MhdIdx& x)
 {
-  if (i < 2 || j < 2 || k < 2 || i > g.isize - 2 || j > g.jsize - 2 || k > g.ksize - 2)
+  if (x.i < 2 || x.j < 2 || x.k < 2 || x.i > g.isize - 2 || x.j > g.jsize - 2 || x.k > g.ksize - 2)
     return;
-  const long long o = i + g.sj * j + g.sk * k, sj = g.sj, sk = g.sk, sv = g.sv;
-  const double* __restrict__ UA = U + sv * IA;
-  const double* __restrict__ UB = U + sv * IB;
-  const double* __restrict__ UC = U + sv * IC;
-  const double* __restrict__ Ex = E;
-  const double* __restrict__ Ey = E + sv;
-  const double* __restrict__ Ez = E + 2 * sv;
-  const bool in_i = i <= g.isize - 3, in_j = j <= g.jsize - 3, in_k = k <= g.ksize - 3;
+  const unsigned c = x.c;
+  const long long sj = x.sj, sk = x.sk, sv = g.sv;
+  const double* __restrict__ UA = U + sv * IA + c;
+  const double* __restrict__ UB = U + sv * IB + c;
+  const double* __restrict__ UC = U + sv * IC + c;
+  const double* __restrict__ E0 = E + tile_off<3>(c);
+  const bool in_i = x.i <= g.isize - 3, in_j = x.j <= g.jsize - 3, in_k = x.k <= g.ksize - 3;
   const double xst = dmin(g.slope_type, 2.0); // slope_unsplit_mhd_3d, MHDBaseFunctor3D.h:600
+  double* __restrict__ Sc = S + tile_off<S_TOTAL>(c);
 
-  const double AL = UA[o], BL = UB[o], CL = UC[o];
-  const double ELL = Ex[o], FLL = Ey[o], GLL = Ez[o];
+  const double AL = UA[0], BL = UB[0], CL = UC[0];
+  const double ELL = E0[0], FLL = E0[TL], GLL = E0[2 * TL];
+  const double* __restrict__ Ei = E + tile_off<3>(c + 1);
+  const double* __restrict__ Ej = E + tile_off<3>(c + x.sj);
+  const double* __restrict__ Ek = E + tile_off<3>(c + x.sk);
   // face-centred half step: AL + sAL0 etc. (:872-877, :889-894) and halved transverse slopes (:810-822)
   if (in_j && in_k) {
-    const double GLR = Ez[o + sj], FLR = Ey[o + sk];
-    S[o + sv * SFA] = AL + (+(GLR - GLL) * dtdy * 0.5 - (FLR - FLL) * dtdz * 0.5);
-    S[o + sv * SDAY] = 0.5 * mhd_slope(xst, UA[o - sj], AL, UA[o + sj]);
-    S[o + sv * SDAZ] = 0.5 * mhd_slope(xst, UA[o - sk], AL, UA[o + sk]);
+    const double GLR = Ej[2 * TL], FLR = Ek[TL];
+    Sc[TL * SFA] = AL + (+(GLR - GLL) * dtdy * 0.5 - (FLR - FLL) * dtdz * 0.5);
+    Sc[TL * SDAY] = 0.5 * mhd_slope(xst, UA[-sj], AL, UA[sj]);
+    Sc[TL * SDAZ] = 0.5 * mhd_slope(xst, UA[-sk], AL, UA[sk]);
   }
   if (in_i && in_k) {
-    const double GRL = Ez[o + 1], ELR = Ex[o + sk];
-    S[o + sv * SFB] = BL + (-(GRL - GLL) * dtdx * 0.5 + (ELR - ELL) * dtdz * 0.5);
-    S[o + sv * SDBX] = 0.5 * mhd_slope(xst, UB[o - 1], BL, UB[o + 1]);
-    S[o + sv * SDBZ] = 0.5 * mhd_slope(xst, UB[o - sk], BL, UB[o + sk]);
+    const double GRL = Ei[2 * TL], ELR = Ek[0];
+    Sc[TL * SFB] = BL + (-(GRL - GLL) * dtdx * 0.5 + (ELR - ELL) * dtdz * 0.5);
+    Sc[TL * SDBX] = 0.5 * mhd_slope(xst, UB[-1], BL, UB[1]);
+    Sc[TL * SDBZ] = 0.5 * mhd_slope(xst, UB[-sk], BL, UB[sk]);
   }
   if (in_i && in_j) {
-    const double FRL = Ey[o + 1], ERL = Ex[o + sj];
-    S[o + sv * SFC] = CL + (+(FRL - FLL) * dtdx * 0.5 - (ERL - ELL) * dtdy * 0.5);
-    S[o + sv * SDCX] = 0.5 * mhd_slope(xst, UC[o - 1], CL, UC[o + 1]);
-    S[o + sv * SDCY] = 0.5 * mhd_slope(xst, UC[o - sj], CL, UC[o + sj]);
+    const double FRL = Ei[TL], ERL = Ej[0];
+    Sc[TL * SFC] = CL + (+(FRL - FLL) * dtdx * 0.5 - (ERL - ELL) * dtdy * 0.5);
+    Sc[TL * SDCX] = 0.5 * mhd_slope(xst, UC[-1], CL, UC[1]);
+    Sc[TL * SDCY] = 0.5 * mhd_slope(xst, UC[-sj], CL, UC[sj]);
   }
   if (!(in_i && in_j && in_k))
     return;
@@ -160,18 +194,25 @@ EK_HD void mhd_stage_trace(const Grid& g, const double* __restrict__ U, const do
   // cell-centred half step
   const double st = g.slope_type;
   const bool use_slopes = (st == 1.0 || st == 2.0); // slope_unsplit_hydro_3d, :379,:470
+  const double* __restrict__ Q0 = Q + tile_off<8>(c);
+  const double* __restrict__ Qxm = Q + tile_off<8>(c - 1);
+  const double* __restrict__ Qxp = Q + tile_off<8>(c + 1);
+  const double* __restrict__ Qym = Q + tile_off<8>(c - x.sj);
+  const double* __restrict__ Qyp = Q + tile_off<8>(c + x.sj);
+  const double* __restrict__ Qzm = Q + tile_off<8>(c - x.sk);
+  const double* __restrict__ Qzp = Q + tile_off<8>(c + x.sk);
   double q[8], dx_[8], dy_[8], dz_[8];
 #pragma unroll
   for (int v = 0; v < 8; ++v) {
-    const double* __restrict__ Qv = Q + sv * v;
-    const double qc = Qv[o];
+    const double qc = Q0[TL * v];
     q[v] = qc;
-    // halved limited slopes (the reference halves them first thing in the trace, :765-806)
-    dx_[v] = (use_slopes && v != IA) ? 0.5 * mhd_slope(st, Qv[o - 1], qc, Qv[o + 1]) : 0.0;
-    dy_[v] = (use_slopes && v != IB) ? 0.5 * mhd_slope(st, Qv[o - sj], qc, Qv[o + sj]) : 0.0;
-    dz_[v] = (use_slopes && v != IC) ? 0.5 * mhd_slope(st, Qv[o - sk], qc, Qv[o + sk]) : 0.0;
+    // halved limited slopes (the reference halves them first thing in the trace, :765-806); the
+    // normal-field slopes (dAx, dBy, dCz) come from the face values instead (:825-827)
+    dx_[v] = (use_slopes && v != IA) ? 0.5 * mhd_slope(st, Qxm[TL * v], qc, Qxp[TL * v]) : 0.0;
+    dy_[v] = (use_slopes && v != IB) ? 0.5 * mhd_slope(st, Qym[TL * v], qc, Qyp[TL * v]) : 0.0;
+    dz_[v] = (use_slopes && v != IC) ? 0.5 * mhd_slope(st, Qzm[TL * v], qc, Qzp[TL * v]) : 0.0;
   }
-  const double AR = UA[o + 1], BR = UB[o + sj], CR = UC[o + sk];
+  const double AR = UA[1], BR = UB[sj], CR = UC[sk];
   const double r = q[ID], p = q[IP], u = q[IU], v = q[IV], w = q[IW], A = q[IA], B = q[IB], C = q[IC];
   const double drx = dx_[ID], dpx = dx_[IP], dux = dx_[IU], dvx = dx_[IV], dwx = dx_[IW], dBx = dx_[IB], dCx = dx_[IC];
   const double dry = dy_[ID], dpy = dy_[IP], duy = dy_[IU], dvy = dy_[IV], dwy = dy_[IW], dAy = dy_[IA], dCy = dy_[IC];
@@ -189,30 +230,29 @@ EK_HD void mhd_stage_trace(const Grid& g, const double* __restrict__ U, const do
   const double sB0 = (v * dAx + A * dvx - u * dBx - B * dux) * dtdx + (v * dCz + C * dvz - w * dBz - B * dwz) * dtdz;
   const double sC0 = (w * dAx + A * dwx - u * dCx - C * dux) * dtdx + (w * dBy + B * dwy - v * dCy - C * dvy) * dtdy;
 
-  double* __restrict__ Sc = S + o;
-  Sc[sv * (SC + ID)] = r + sr0;
-  Sc[sv * (SC + IP)] = p + sp0;
-  Sc[sv * (SC + IU)] = u + su0;
-  Sc[sv * (SC + IV)] = v + sv0;
-  Sc[sv * (SC + IW)] = w + sw0;
-  Sc[sv * (SC + IA)] = A + sA0;
-  Sc[sv * (SC + IB)] = B + sB0;
-  Sc[sv * (SC + IC)] = C + sC0;
-  Sc[sv * (SX + 0)] = drx; Sc[sv * (SX + 1)] = dpx; Sc[sv * (SX + 2)] = dux; Sc[sv * (SX + 3)] = dvx; Sc[sv * (SX + 4)] = dwx;
-  Sc[sv * (SX + 5)] = dBx; Sc[sv * (SX + 6)] = dCx;
-  Sc[sv * (SY + 0)] = dry; Sc[sv * (SY + 1)] = dpy; Sc[sv * (SY + 2)] = duy; Sc[sv * (SY + 3)] = dvy; Sc[sv * (SY + 4)] = dwy;
-  Sc[sv * (SY + 5)] = dAy; Sc[sv * (SY + 6)] = dCy;
-  Sc[sv * (SZ + 0)] = drz; Sc[sv * (SZ + 1)] = dpz; Sc[sv * (SZ + 2)] = duz; Sc[sv * (SZ + 3)] = dvz; Sc[sv * (SZ + 4)] = dwz;
-  Sc[sv * (SZ + 5)] = dAz; Sc[sv * (SZ + 6)] = dBz;
+  Sc[TL * (SC + ID)] = r + sr0;
+  Sc[TL * (SC + IP)] = p + sp0;
+  Sc[TL * (SC + IU)] = u + su0;
+  Sc[TL * (SC + IV)] = v + sv0;
+  Sc[TL * (SC + IW)] = w + sw0;
+  Sc[TL * (SC + IA)] = A + sA0;
+  Sc[TL * (SC + IB)] = B + sB0;
+  Sc[TL * (SC + IC)] = C + sC0;
+  Sc[TL * (SX + 0)] = drx; Sc[TL * (SX + 1)] = dpx; Sc[TL * (SX + 2)] = dux; Sc[TL * (SX + 3)] = dvx; Sc[TL * (SX + 4)] = dwx;
+  Sc[TL * (SX + 5)] = dBx; Sc[TL * (SX + 6)] = dCx;
+  Sc[TL * (SY + 0)] = dry; Sc[TL * (SY + 1)] = dpy; Sc[TL * (SY + 2)] = duy; Sc[TL * (SY + 3)] = dvy; Sc[TL * (SY + 4)] = dwy;
+  Sc[TL * (SY + 5)] = dAy; Sc[TL * (SY + 6)] = dCy;
+  Sc[TL * (SZ + 0)] = drz; Sc[TL * (SZ + 1)] = dpz; Sc[TL * (SZ + 2)] = duz; Sc[TL * (SZ + 3)] = dvz; Sc[TL * (SZ + 4)] = dwz;
+  Sc[TL * (SZ + 5)] = dAz; Sc[TL * (SZ + 6)] = dBz;
 }
 
 // ---- stage R ------------------------------------------------------------------------------------
 // one side of a face: cell state +/- halved slope along the face normal, floors as :896-975
 // D: normal direction; sgn = +1 (upper face of the cell = left state of the face), -1 (lower face)
+// Sc: tile pointer of the cell (variable v at Sc[TL*v])
 template <int D>
-EK_HD MhdSide mhd_face_side(const Grid& g, const double* __restrict__ S, long long o, double sgn)
+EK_HD MhdSide mhd_face_side(const Grid& g, const double* __restrict__ Sc, double sgn)
 {
-  const long long sv = g.sv;
   constexpr int SD = (D == 0) ? SX : (D == 1) ? SY : SZ;
   // velocity / field components in the face-normal frame (the reference swaps IU<->IV, IA<->IB for y
   // and IU<->IW, IA<->IC for z, MHDRunFunctors3D.h:1857-1890)
@@ -222,47 +262,46 @@ EK_HD MhdSide mhd_face_side(const Grid& g, const double* __restrict__ S, long lo
   constexpr int BT1 = (D == 0) ? IB : (D == 1) ? IA : IB;
   constexpr int BT2 = (D == 0) ? IC : (D == 1) ? IC : IA;
   // slot of the two transverse-field slopes inside the 7-slope group of direction D:
-  //   x: (.., dBx, dCx) -> B at 5, C at 6;  y: (.., dAy, dCy) -> A at 5, C at 6;  z: (.., dAz, dBz) -> A at 5, B at 6
+  //   x: (.., dBx, dCx)   y: (.., dAy, dCy)   z: (.., dAz, dBz)
   constexpr int KT1 = (D == 2) ? 6 : 5; // z: bt1 = B (slot 6);  x: bt1 = B (slot 5);  y: bt1 = A (slot 5)
   constexpr int KT2 = (D == 2) ? 5 : 6; // z: bt2 = A (slot 5);  x: bt2 = C (slot 6);  y: bt2 = C (slot 6)
-  const double* __restrict__ Sc = S + o;
   MhdSide s;
-  s.r = dmax(g.smallr, Sc[sv * (SC + ID)] + sgn * Sc[sv * (SD + 0)]);
-  s.p = dmax(g.smallp, Sc[sv * (SC + IP)] + sgn * Sc[sv * (SD + 1)]);
-  s.un = Sc[sv * (SC + VN)] + sgn * Sc[sv * (SD + 2 + (VN - IU))];
-  s.ut1 = Sc[sv * (SC + VT1)] + sgn * Sc[sv * (SD + 2 + (VT1 - IU))];
-  s.ut2 = Sc[sv * (SC + VT2)] + sgn * Sc[sv * (SD + 2 + (VT2 - IU))];
-  s.bt1 = Sc[sv * (SC + BT1)] + sgn * Sc[sv * (SD + KT1)];
-  s.bt2 = Sc[sv * (SC + BT2)] + sgn * Sc[sv * (SD + KT2)];
+  s.r = dmax(g.smallr, Sc[TL * (SC + ID)] + sgn * Sc[TL * (SD + 0)]);
+  s.p = dmax(g.smallp, Sc[TL * (SC + IP)] + sgn * Sc[TL * (SD + 1)]);
+  s.un = Sc[TL * (SC + VN)] + sgn * Sc[TL * (SD + 2 + (VN - IU))];
+  s.ut1 = Sc[TL * (SC + VT1)] + sgn * Sc[TL * (SD + 2 + (VT1 - IU))];
+  s.ut2 = Sc[TL * (SC + VT2)] + sgn * Sc[TL * (SD + 2 + (VT2 - IU))];
+  s.bt1 = Sc[TL * (SC + BT1)] + sgn * Sc[TL * (SD + KT1)];
+  s.bt2 = Sc[TL * (SC + BT2)] + sgn * Sc[TL * (SD + KT2)];
   return s;
 }
 
-// flux through the lower D-face of cell o, stored as (mass, energy, mom_x, mom_y, mom_z)
+// flux through the lower D-face of cell c: f = (mass, energy, mom_x, mom_y, mom_z)
 template <int D, int RS>
-EK_HD void mhd_face_flux(const Grid& g, const double* __restrict__ S, long long o, double* __restrict__ F)
+EK_HD void mhd_face_flux(const Grid& g, const double* __restrict__ S, const MhdIdx& x, double* __restrict__ fout)
 {
-  const long long sv = g.sv;
-  const long long sd = (D == 0) ? 1 : (D == 1) ? g.sj : g.sk;
-  const MhdSide L = mhd_face_side<D>(g, S, o - sd, +1.0);
-  const MhdSide R = mhd_face_side<D>(g, S, o, -1.0);
-  const double a = S[o + sv * (SFA + D)]; // both sides carry the same half-step face field
+  const unsigned sd = (D == 0) ? 1u : (D == 1) ? x.sj : x.sk;
+  const double* __restrict__ Sc = S + tile_off<S_TOTAL>(x.c);
+  const double* __restrict__ Sm = S + tile_off<S_TOTAL>(x.c - sd);
+  const MhdSide L = mhd_face_side<D>(g, Sm, +1.0);
+  const MhdSide R = mhd_face_side<D>(g, Sc, -1.0);
+  const double a = Sc[TL * (SFA + D)]; // both sides carry the same half-step face field
   double f[5];
   mhd_riemann<RS>(g, L, R, a, f);
-  double* __restrict__ Fd = F + o + sv * (5 * D);
-  Fd[0] = f[0];
-  Fd[sv] = f[1];
+  fout[0] = f[0];
+  fout[1] = f[1];
   if (D == 0) {
-    Fd[2 * sv] = f[2]; Fd[3 * sv] = f[3]; Fd[4 * sv] = f[4];
+    fout[2] = f[2]; fout[3] = f[3]; fout[4] = f[4];
   } else if (D == 1) {
-    Fd[2 * sv] = f[3]; Fd[3 * sv] = f[2]; Fd[4 * sv] = f[4];
+    fout[2] = f[3]; fout[3] = f[2]; fout[4] = f[4];
   } else {
-    Fd[2 * sv] = f[4]; Fd[3 * sv] = f[3]; Fd[4 * sv] = f[2];
+    fout[2] = f[4]; fout[3] = f[3]; fout[4] = f[2];
   }
 }
 
-// one corner state of the edge along D3: cell at o, slopes applied with signs s1 (along D1), s2 (along D2)
+// one corner state of the edge along D3: cell tile pointer Sc, slopes applied with signs s1 (along D1), s2 (along D2)
 template <int D3>
-EK_HD MhdCorner mhd_edge_corner(const Grid& g, const double* __restrict__ S, long long o, double s1, double s2, double a, double b)
+EK_HD MhdCorner mhd_edge_corner(const Grid& g, const double* __restrict__ Sc, double s1, double s2, double a, double b)
 {
   constexpr int D1 = (D3 + 1) % 3, D2 = (D3 + 2) % 3;
   constexpr int S1 = (D1 == 0) ? SX : (D1 == 1) ? SY : SZ;
@@ -271,107 +310,123 @@ EK_HD MhdCorner mhd_edge_corner(const Grid& g, const double* __restrict__ S, lon
   //   group x = (B,C) at (5,6), group y = (A,C) at (5,6), group z = (A,B) at (5,6)
   constexpr int K1 = (D1 == 0) ? (D3 == 1 ? 5 : 6) : (D1 == 1) ? (D3 == 0 ? 5 : 6) : (D3 == 0 ? 5 : 6);
   constexpr int K2 = (D2 == 0) ? (D3 == 1 ? 5 : 6) : (D2 == 1) ? (D3 == 0 ? 5 : 6) : (D3 == 0 ? 5 : 6);
-  const long long sv = g.sv;
-  const double* __restrict__ Sc = S + o;
   MhdCorner c;
-  c.r = dmax(g.smallr, Sc[sv * (SC + ID)] + (s1 * Sc[sv * (S1 + 0)] + s2 * Sc[sv * (S2 + 0)]));
-  c.p = dmax(g.smallp, Sc[sv * (SC + IP)] + (s1 * Sc[sv * (S1 + 1)] + s2 * Sc[sv * (S2 + 1)]));
-  c.u = Sc[sv * (SC + IU + D1)] + (s1 * Sc[sv * (S1 + 2 + D1)] + s2 * Sc[sv * (S2 + 2 + D1)]);
-  c.v = Sc[sv * (SC + IU + D2)] + (s1 * Sc[sv * (S1 + 2 + D2)] + s2 * Sc[sv * (S2 + 2 + D2)]);
-  c.c = Sc[sv * (SC + IA + D3)] + (s1 * Sc[sv * (S1 + K1)] + s2 * Sc[sv * (S2 + K2)]);
+  c.r = dmax(g.smallr, Sc[TL * (SC + ID)] + (s1 * Sc[TL * (S1 + 0)] + s2 * Sc[TL * (S2 + 0)]));
+  c.p = dmax(g.smallp, Sc[TL * (SC + IP)] + (s1 * Sc[TL * (S1 + 1)] + s2 * Sc[TL * (S2 + 1)]));
+  c.u = Sc[TL * (SC + IU + D1)] + (s1 * Sc[TL * (S1 + 2 + D1)] + s2 * Sc[TL * (S2 + 2 + D1)]);
+  c.v = Sc[TL * (SC + IU + D2)] + (s1 * Sc[TL * (S1 + 2 + D2)] + s2 * Sc[TL * (S2 + 2 + D2)]);
+  c.c = Sc[TL * (SC + IA + D3)] + (s1 * Sc[TL * (S1 + K1)] + s2 * Sc[TL * (S2 + K2)]);
   c.a = a;
   c.b = b;
   return c;
 }
 
-// EMF at the lower edge of cell o that runs along D3 (compute_emf<EMFX|EMFY|EMFZ> with the corner
+// EMF at the lower edge of cell c that runs along D3 (compute_emf<EMFX|EMFY|EMFZ> with the corner
 // assignment of ComputeEmfAndStoreFunctor3D, MHDRunFunctors3D.h:2199-2226)
 template <int D3>
-EK_HD double mhd_edge_emf(const Grid& g, const double* __restrict__ S, long long o)
+EK_HD double mhd_edge_emf(const Grid& g, const double* __restrict__ S, const MhdIdx& x)
 {
   constexpr int D1 = (D3 + 1) % 3, D2 = (D3 + 2) % 3;
-  const long long sv = g.sv;
-  const long long s1 = (D1 == 0) ? 1 : (D1 == 1) ? g.sj : g.sk;
-  const long long s2 = (D2 == 0) ? 1 : (D2 == 1) ? g.sj : g.sk;
-  // face field B_D1 lives on D1-faces and varies along D2; its transverse slope along D2
+  const unsigned s1 = (D1 == 0) ? 1u : (D1 == 1) ? x.sj : x.sk;
+  const unsigned s2 = (D2 == 0) ? 1u : (D2 == 1) ? x.sj : x.sk;
+  // face field B_D1 lives on D1-faces and varies along D2 (and vice versa); halved transverse slopes
   constexpr int F1 = SFA + D1, F2 = SFA + D2;
   constexpr int DF1 = (D1 == 0) ? (D2 == 1 ? SDAY : SDAZ) : (D1 == 1) ? (D2 == 0 ? SDBX : SDBZ) : (D2 == 0 ? SDCX : SDCY);
   constexpr int DF2 = (D2 == 0) ? (D1 == 1 ? SDAY : SDAZ) : (D2 == 1) ? (D1 == 0 ? SDBX : SDBZ) : (D1 == 0 ? SDCX : SDCY);
-  const double aLow = S[o - s2 + sv * F1] + S[o - s2 + sv * DF1]; // aLL = aRL
-  const double aHigh = S[o + sv * F1] - S[o + sv * DF1];          // aLR = aRR
-  const double bLow = S[o - s1 + sv * F2] + S[o - s1 + sv * DF2]; // bLL = bLR
-  const double bHigh = S[o + sv * F2] - S[o + sv * DF2];          // bRL = bRR
-  const MhdCorner LL = mhd_edge_corner<D3>(g, S, o - s1 - s2, +1.0, +1.0, aLow, bLow);
-  const MhdCorner RL = mhd_edge_corner<D3>(g, S, o - s2, -1.0, +1.0, aLow, bHigh);
-  const MhdCorner LR = mhd_edge_corner<D3>(g, S, o - s1, +1.0, -1.0, aHigh, bLow);
-  const MhdCorner RR = mhd_edge_corner<D3>(g, S, o, -1.0, -1.0, aHigh, bHigh);
+  const double* __restrict__ S00 = S + tile_off<S_TOTAL>(x.c);
+  const double* __restrict__ S10 = S + tile_off<S_TOTAL>(x.c - s1);
+  const double* __restrict__ S01 = S + tile_off<S_TOTAL>(x.c - s2);
+  const double* __restrict__ S11 = S + tile_off<S_TOTAL>(x.c - s1 - s2);
+  const double aLow = S01[TL * F1] + S01[TL * DF1];  // aLL = aRL
+  const double aHigh = S00[TL * F1] - S00[TL * DF1]; // aLR = aRR
+  const double bLow = S10[TL * F2] + S10[TL * DF2];  // bLL = bLR
+  const double bHigh = S00[TL * F2] - S00[TL * DF2]; // bRL = bRR
+  const MhdCorner LL = mhd_edge_corner<D3>(g, S11, +1.0, +1.0, aLow, bLow);
+  const MhdCorner RL = mhd_edge_corner<D3>(g, S01, -1.0, +1.0, aLow, bHigh);
+  const MhdCorner LR = mhd_edge_corner<D3>(g, S10, +1.0, -1.0, aHigh, bLow);
+  const MhdCorner RR = mhd_edge_corner<D3>(g, S00, -1.0, -1.0, aHigh, bHigh);
   return mhd_emf2d_hlld(g, LL, RL, LR, RR);
 }
 
-EK_HD bool mhd_stage_r_active(const Grid& g, int i, int j, int k)
+EK_HD bool mhd_stage_r_active(const Grid& g, const MhdIdx& x)
 {
   const int gw = g.gw;
-  return i >= gw && j >= gw && k >= gw && i <= g.isize - gw && j <= g.jsize - gw && k <= g.ksize - gw;
+  return x.i >= gw && x.j >= gw && x.k >= gw && x.i <= g.isize - gw && x.j <= g.jsize - gw && x.k <= g.ksize - gw;
 }
 
 template <int RS>
-EK_HD void mhd_stage_fluxes(const Grid& g, const double* __restrict__ S, double* __restrict__ F, int i, int j, int k)
+EK_HD void mhd_stage_fluxes(const Grid& g, const double* __restrict__ S, double* __restrict__ F, const MhdIdx& x)
 {
-  if (!mhd_stage_r_active(g, i, j, k))
+  if (!mhd_stage_r_active(g, x))
     return;
-  const long long o = i + g.sj * j + g.sk * k;
-  mhd_face_flux<0, RS>(g, S, o, F);
-  mhd_face_flux<1, RS>(g, S, o, F);
-  mhd_face_flux<2, RS>(g, S, o, F);
+  double* __restrict__ Fc = F + tile_off<15>(x.c);
+  double f[5];
+  mhd_face_flux<0, RS>(g, S, x, f);
+#pragma unroll
+  for (int v = 0; v < 5; ++v)
+    Fc[TL * v] = f[v];
+  mhd_face_flux<1, RS>(g, S, x, f);
+#pragma unroll
+  for (int v = 0; v < 5; ++v)
+    Fc[TL * (5 + v)] = f[v];
+  mhd_face_flux<2, RS>(g, S, x, f);
+#pragma unroll
+  for (int v = 0; v < 5; ++v)
+    Fc[TL * (10 + v)] = f[v];
 }
 
-EK_HD void mhd_stage_emfs(const Grid& g, const double* __restrict__ S, double* __restrict__ EMF, int i, int j, int k)
+EK_HD void mhd_stage_emfs(const Grid& g, const double* __restrict__ S, double* __restrict__ EMF, const MhdIdx& x)
 {
-  if (!mhd_stage_r_active(g, i, j, k))
+  if (!mhd_stage_r_active(g, x))
     return;
-  const long long o = i + g.sj * j + g.sk * k;
-  EMF[o] = mhd_edge_emf<0>(g, S, o);
-  EMF[o + g.sv] = mhd_edge_emf<1>(g, S, o);
-  EMF[o + 2 * g.sv] = mhd_edge_emf<2>(g, S, o);
+  double* __restrict__ Ec = EMF + tile_off<3>(x.c);
+  Ec[0] = mhd_edge_emf<0>(g, S, x);
+  Ec[TL] = mhd_edge_emf<1>(g, S, x);
+  Ec[2 * TL] = mhd_edge_emf<2>(g, S, x);
 }
 
 // ---- stage U ------------------------------------------------------------------------------------
 // UpdateFunctor3D_MHD + UpdateEmfFunctor3D on one interior cell, same accumulation order
 EK_HD void mhd_stage_update(const Grid& g, const double* __restrict__ Uin, const double* __restrict__ F, const double* __restrict__ EMF,
-                            double* __restrict__ Uout, double dtdx, double dtdy, double dtdz, int i, int j, int k)
+                            double* __restrict__ Uout, double dtdx, double dtdy, double dtdz, const MhdIdx& x)
 {
   const int gw = g.gw;
-  if (i < gw || j < gw || k < gw || i >= g.isize - gw || j >= g.jsize - gw || k >= g.ksize - gw)
+  if (x.i < gw || x.j < gw || x.k < gw || x.i >= g.isize - gw || x.j >= g.jsize - gw || x.k >= g.ksize - gw)
     return;
-  const long long o = i + g.sj * j + g.sk * k, sj = g.sj, sk = g.sk, sv = g.sv;
+  const unsigned c = x.c;
+  const long long sv = g.sv;
+  const double* __restrict__ F0 = F + tile_off<15>(c);
+  const double* __restrict__ Fi = F + tile_off<15>(c + 1);
+  const double* __restrict__ Fj = F + tile_off<15>(c + x.sj);
+  const double* __restrict__ Fk = F + tile_off<15>(c + x.sk);
+  const double* __restrict__ Uc = Uin + c;
+  double* __restrict__ Oc = Uout + c;
 #pragma unroll
   for (int v = 0; v < 5; ++v) {
-    double u = Uin[o + sv * v];
-    const double* __restrict__ Fx = F + sv * v;
-    const double* __restrict__ Fy = F + sv * (5 + v);
-    const double* __restrict__ Fz = F + sv * (10 + v);
-    u += Fx[o] * dtdx;
-    u -= Fx[o + 1] * dtdx;
-    u += Fy[o] * dtdy;
-    u -= Fy[o + sj] * dtdy;
-    u += Fz[o] * dtdz;
-    u -= Fz[o + sk] * dtdz;
-    Uout[o + sv * v] = u;
+    double u = Uc[sv * v];
+    u += F0[TL * v] * dtdx;
+    u -= Fi[TL * v] * dtdx;
+    u += F0[TL * (5 + v)] * dtdy;
+    u -= Fj[TL * (5 + v)] * dtdy;
+    u += F0[TL * (10 + v)] * dtdz;
+    u -= Fk[TL * (10 + v)] * dtdz;
+    Oc[sv * v] = u;
   }
-  const double* __restrict__ Ex = EMF;
-  const double* __restrict__ Ey = EMF + sv;
-  const double* __restrict__ Ez = EMF + 2 * sv;
-  double A = Uin[o + sv * IA], B = Uin[o + sv * IB], C = Uin[o + sv * IC];
-  const double ex = Ex[o], ey = Ey[o], ez = Ez[o];
-  A += (Ez[o + sj] - ez) * dtdy;
-  B -= (Ez[o + 1] - ez) * dtdx;
-  A -= (Ey[o + sk] - ey) * dtdz;
-  B += (Ex[o + sk] - ex) * dtdz;
-  C += (Ey[o + 1] - ey) * dtdx;
-  C -= (Ex[o + sj] - ex) * dtdy;
-  Uout[o + sv * IA] = A;
-  Uout[o + sv * IB] = B;
-  Uout[o + sv * IC] = C;
+  const double* __restrict__ E0 = EMF + tile_off<3>(c);
+  const double* __restrict__ Ei = EMF + tile_off<3>(c + 1);
+  const double* __restrict__ Ej = EMF + tile_off<3>(c + x.sj);
+  const double* __restrict__ Ek = EMF + tile_off<3>(c + x.sk);
+  double A = Uc[sv * IA], B = Uc[sv * IB], C = Uc[sv * IC];
+  const double ex = E0[0], ey = E0[TL], ez = E0[2 * TL];
+  A += (Ej[2 * TL] - ez) * dtdy;
+  B -= (Ei[2 * TL] - ez) * dtdx;
+  A -= (Ek[TL] - ey) * dtdz;
+  B += (Ek[0] - ex) * dtdz;
+  C += (Ei[TL] - ey) * dtdx;
+  C -= (Ej[0] - ex) * dtdy;
+  Oc[sv * IA] = A;
+  Oc[sv * IB] = B;
+  Oc[sv * IC] = C;
 }
 
 } // namespace ek

@@ -14,15 +14,21 @@ struct MhdArgs {
   TimeState* ts;
 };
 
-__device__ __forceinline__ bool mhd_cell_of_thread(const Grid& g, int& i, int& j, int& k)
+__device__ __forceinline__ bool mhd_cell_of_thread(const Grid& g, MhdIdx& x)
 {
-  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= g.sv)
+  const unsigned c = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned sj = (unsigned)g.isize, sk = (unsigned)g.sk;
+  x.c = c;
+  x.sj = sj;
+  x.sk = sk;
+  if (c >= (unsigned)g.sv)
     return false;
-  k = (int)(c / g.sk);
-  const int r = (int)(c - (long long)k * g.sk);
-  j = r / g.isize;
-  i = r - j * g.isize;
+  const unsigned k = c / sk;
+  const unsigned r = c - k * sk;
+  const unsigned j = r / sj;
+  x.k = (int)k;
+  x.j = (int)j;
+  x.i = (int)(r - j * sj);
   return true;
 }
 
@@ -32,10 +38,10 @@ __global__ void __launch_bounds__(256) mhd_prims_kernel(const MhdArgs a, const i
   if (a.ts->finished)
     return;
   const MhdWork w = mhd_work_split(a.work, a.g.sv);
-  int i, j, k;
+  MhdIdx x;
   double m = 0.0;
-  if (mhd_cell_of_thread(a.g, i, j, k))
-    m = mhd_stage_prims(a.g, a.Uin, w.Q, i, j, k);
+  if (mhd_cell_of_thread(a.g, x))
+    m = mhd_stage_prims(a.g, a.Uin, w.Q, x);
   if (!do_invdt)
     return;
   __shared__ double red[8];
@@ -56,9 +62,9 @@ __global__ void __launch_bounds__(256) mhd_elec_kernel(const MhdArgs a)
   if (a.ts->finished)
     return;
   const MhdWork w = mhd_work_split(a.work, a.g.sv);
-  int i, j, k;
-  if (mhd_cell_of_thread(a.g, i, j, k))
-    mhd_stage_elec(a.g, a.Uin, w.Q, w.E, i, j, k);
+  MhdIdx x;
+  if (mhd_cell_of_thread(a.g, x))
+    mhd_stage_elec(a.g, a.Uin, w.Q, w.E, x);
 }
 
 __global__ void __launch_bounds__(256) mhd_trace_kernel(const MhdArgs a)
@@ -67,9 +73,9 @@ __global__ void __launch_bounds__(256) mhd_trace_kernel(const MhdArgs a)
     return;
   const MhdWork w = mhd_work_split(a.work, a.g.sv);
   const double dt = a.ts->dt;
-  int i, j, k;
-  if (mhd_cell_of_thread(a.g, i, j, k))
-    mhd_stage_trace(a.g, a.Uin, w.Q, w.E, w.S, dt / a.g.dx, dt / a.g.dy, dt / a.g.dz, i, j, k);
+  MhdIdx x;
+  if (mhd_cell_of_thread(a.g, x))
+    mhd_stage_trace(a.g, a.Uin, w.Q, w.E, w.S, dt / a.g.dx, dt / a.g.dy, dt / a.g.dz, x);
 }
 
 template <int RS>
@@ -78,9 +84,9 @@ __global__ void __launch_bounds__(128) mhd_flux_kernel(const MhdArgs a)
   if (a.ts->finished)
     return;
   const MhdWork w = mhd_work_split(a.work, a.g.sv);
-  int i, j, k;
-  if (mhd_cell_of_thread(a.g, i, j, k))
-    mhd_stage_fluxes<RS>(a.g, w.S, w.F, i, j, k);
+  MhdIdx x;
+  if (mhd_cell_of_thread(a.g, x))
+    mhd_stage_fluxes<RS>(a.g, w.S, w.F, x);
 }
 
 __global__ void __launch_bounds__(128) mhd_emf_kernel(const MhdArgs a)
@@ -88,9 +94,9 @@ __global__ void __launch_bounds__(128) mhd_emf_kernel(const MhdArgs a)
   if (a.ts->finished)
     return;
   const MhdWork w = mhd_work_split(a.work, a.g.sv);
-  int i, j, k;
-  if (mhd_cell_of_thread(a.g, i, j, k))
-    mhd_stage_emfs(a.g, w.S, w.EMF, i, j, k);
+  MhdIdx x;
+  if (mhd_cell_of_thread(a.g, x))
+    mhd_stage_emfs(a.g, w.S, w.EMF, x);
 }
 
 __global__ void __launch_bounds__(256) mhd_update_kernel(const MhdArgs a)
@@ -99,9 +105,9 @@ __global__ void __launch_bounds__(256) mhd_update_kernel(const MhdArgs a)
     return;
   const MhdWork w = mhd_work_split(a.work, a.g.sv);
   const double dt = a.ts->dt;
-  int i, j, k;
-  if (mhd_cell_of_thread(a.g, i, j, k))
-    mhd_stage_update(a.g, a.Uin, w.F, w.EMF, a.Uout, dt / a.g.dx, dt / a.g.dy, dt / a.g.dz, i, j, k);
+  MhdIdx x;
+  if (mhd_cell_of_thread(a.g, x))
+    mhd_stage_update(a.g, a.Uin, w.F, w.EMF, a.Uout, dt / a.g.dx, dt / a.g.dy, dt / a.g.dz, x);
 }
 
 } // namespace ek

@@ -6,7 +6,7 @@ namespace ek {
 
 size_t mhd_work_bytes(const Grid& g)
 {
-  return (size_t)W_TOTAL * (size_t)g.sv * sizeof(double);
+  return (size_t)W_TOTAL * (size_t)mhd_padded_cells(g.sv) * sizeof(double);
 }
 
 static MhdArgs make_args(Ctx& c, const double* Uin, double* Uout)

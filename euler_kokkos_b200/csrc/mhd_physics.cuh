@@ -79,26 +79,27 @@ EK_HD double mhd_cell_invdt(const Grid& g, const double* __restrict__ q)
   const double c2 = g.gamma0 * q[IP] * rd;
   const double d2 = 0.5 * (b2 * rd + c2);
   const double d22 = d2 * d2, c2r = c2 * rd;
-  const double cfx = sqrt(d2 + sqrt(dmax(d22 - c2r * a * a, 0.0)));
-  const double cfy = sqrt(d2 + sqrt(dmax(d22 - c2r * b * b, 0.0)));
-  const double cfz = sqrt(d2 + sqrt(dmax(d22 - c2r * c * c, 0.0)));
-  return (cfx + fabs(q[IU])) / g.dx + (cfy + fabs(q[IV])) / g.dy + (cfz + fabs(q[IW])) / g.dz;
+  const double cfx = sqrt_fast(d2 + sqrt_fast(dmax(d22 - c2r * a * a, 0.0)));
+  const double cfy = sqrt_fast(d2 + sqrt_fast(dmax(d22 - c2r * b * b, 0.0)));
+  const double cfz = sqrt_fast(d2 + sqrt_fast(dmax(d22 - c2r * c * c, 0.0)));
+  return (cfx + fabs(q[IU])) * g.invdx + (cfy + fabs(q[IV])) * g.invdy + (cfz + fabs(q[IW])) * g.invdz;
 }
 
-// fast magnetosonic speed along the face normal: bn2 = Bn^2, bt2sum = Bt1^2 + Bt2^2
-EK_HD double mhd_fast_speed(double gamma0, double r, double p, double bn2, double bt2sum)
+// SQUARE of the fast magnetosonic speed along the face normal: bn2 = Bn^2, bt2sum = Bt1^2 + Bt2^2.
+// Callers take the max over states first and the square root once (sqrt is monotonic).
+EK_HD double mhd_fast_speed2(double gamma0, double r, double p, double bn2, double bt2sum)
 {
   const double rd = rcp_fast(r);
   const double c2 = gamma0 * p * rd;
   const double d2 = 0.5 * ((bn2 + bt2sum) * rd + c2);
-  return sqrt(d2 + sqrt(dmax(d2 * d2 - c2 * bn2 * rd, 0.0)));
+  return d2 + sqrt_fast(dmax(d2 * d2 - c2 * bn2 * rd, 0.0));
 }
 
 // ---- HLLD (Miyoshi & Kusano 2005), hydro components of the flux only --------------------------
 // a = normal field (already the mean of both sides).  f = (mass, energy, normal, t1, t2 momentum).
 EK_HD void mhd_hlld(const Grid& g, const MhdSide& L, const MhdSide& R, double a, double* __restrict__ f)
 {
-  const double entho = 1.0 / (g.gamma0 - 1.0);
+  const double entho = g.entho;
   const double sgnm = (a >= 0.0) ? 1.0 : -1.0;
   const double a2 = a * a;
 
@@ -118,7 +119,7 @@ EK_HD void mhd_hlld(const Grid& g, const MhdSide& L, const MhdSide& R, double a,
   const double ptotr = pr + emagr;
   const double vdotbr = ur * a + vr * br + wr * cr;
 
-  const double cfmax = dmax(mhd_fast_speed(g.gamma0, rl, pl, a2, bt2l), mhd_fast_speed(g.gamma0, rr, pr, a2, bt2r));
+  const double cfmax = sqrt_fast(dmax(mhd_fast_speed2(g.gamma0, rl, pl, a2, bt2l), mhd_fast_speed2(g.gamma0, rr, pr, a2, bt2r)));
   const double sl = dmin(ul, ur) - cfmax;
   const double sr = dmax(ul, ur) + cfmax;
 
@@ -226,13 +227,13 @@ EK_HD void mhd_side_flux(double entho, const MhdSide& s, double a, double* __res
 // MHD HLL (RiemannSolvers_MHD.h:29-64)
 EK_HD void mhd_hll(const Grid& g, const MhdSide& L, const MhdSide& R, double a, double* __restrict__ f)
 {
-  const double entho = 1.0 / (g.gamma0 - 1.0);
+  const double entho = g.entho;
   double ul[5], fl[5], ur[5], fr[5];
   mhd_side_flux(entho, L, a, ul, fl);
   mhd_side_flux(entho, R, a, ur, fr);
   const double a2 = a * a;
-  const double cmax = dmax(mhd_fast_speed(g.gamma0, L.r, L.p, a2, L.bt1 * L.bt1 + L.bt2 * L.bt2),
-                           mhd_fast_speed(g.gamma0, R.r, R.p, a2, R.bt1 * R.bt1 + R.bt2 * R.bt2));
+  const double cmax = sqrt_fast(dmax(mhd_fast_speed2(g.gamma0, L.r, L.p, a2, L.bt1 * L.bt1 + L.bt2 * L.bt2),
+                                     mhd_fast_speed2(g.gamma0, R.r, R.p, a2, R.bt1 * R.bt1 + R.bt2 * R.bt2)));
   const double sl = dmin(dmin(L.un, R.un) - cmax, 0.0);
   const double sr = dmax(dmax(L.un, R.un) + cmax, 0.0);
   const double inv = rcp_fast(sr - sl);
@@ -244,13 +245,13 @@ EK_HD void mhd_hll(const Grid& g, const MhdSide& L, const MhdSide& R, double a, 
 // MHD local Lax-Friedrichs (RiemannSolvers_MHD.h:80-108)
 EK_HD void mhd_llf(const Grid& g, const MhdSide& L, const MhdSide& R, double a, double* __restrict__ f)
 {
-  const double entho = 1.0 / (g.gamma0 - 1.0);
+  const double entho = g.entho;
   double ul[5], fl[5], ur[5], fr[5];
   mhd_side_flux(entho, L, a, ul, fl);
   mhd_side_flux(entho, R, a, ur, fr);
   const double a2 = a * a;
-  const double cl = mhd_fast_speed(g.gamma0, L.r, L.p, a2, L.bt1 * L.bt1 + L.bt2 * L.bt2) + fabs(L.un);
-  const double cr = mhd_fast_speed(g.gamma0, R.r, R.p, a2, R.bt1 * R.bt1 + R.bt2 * R.bt2) + fabs(R.un);
+  const double cl = sqrt_fast(mhd_fast_speed2(g.gamma0, L.r, L.p, a2, L.bt1 * L.bt1 + L.bt2 * L.bt2)) + fabs(L.un);
+  const double cr = sqrt_fast(mhd_fast_speed2(g.gamma0, R.r, R.p, a2, R.bt1 * R.bt1 + R.bt2 * R.bt2)) + fabs(R.un);
   const double vel = dmax(cl, cr);
 #pragma unroll
   for (int v = 0; v < 5; ++v)
@@ -285,12 +286,12 @@ EK_HD double mhd_emf2d_hlld(const Grid& g, const MhdCorner& LL, const MhdCorner&
     const double c2 = gamma0 * s.p * rd;
     const double d2 = 0.5 * (bb * rd + c2);
     const double d22 = d2 * d2, c2r = c2 * rd;
-    cfx[n] = sqrt(d2 + sqrt(dmax(d22 - c2r * a2, 0.0)));
-    cfy[n] = sqrt(d2 + sqrt(dmax(d22 - c2r * b2, 0.0)));
+    cfx[n] = d2 + sqrt_fast(dmax(d22 - c2r * a2, 0.0)); // squares: the square root is taken after the max
+    cfy[n] = d2 + sqrt_fast(dmax(d22 - c2r * b2, 0.0));
     ptot[n] = s.p + 0.5 * bb;
   }
-  const double cxm = dmax(dmax(cfx[0], cfx[1]), dmax(cfx[2], cfx[3]));
-  const double cym = dmax(dmax(cfy[0], cfy[1]), dmax(cfy[2], cfy[3]));
+  const double cxm = sqrt_fast(dmax(dmax(cfx[0], cfx[1]), dmax(cfx[2], cfx[3])));
+  const double cym = sqrt_fast(dmax(dmax(cfy[0], cfy[1]), dmax(cfy[2], cfy[3])));
   const double SL = dmin(dmin(LL.u, LR.u), dmin(RL.u, RR.u)) - cxm;
   const double SR = dmax(dmax(LL.u, LR.u), dmax(RL.u, RR.u)) + cxm;
   const double SB = dmin(dmin(LL.v, LR.v), dmin(RL.v, RR.v)) - cym;

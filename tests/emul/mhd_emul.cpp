@@ -11,17 +11,27 @@
 
 using namespace ek;
 
+static MhdIdx idx(const Grid& g, int i, int j, int k)
+{
+  MhdIdx x;
+  x.sj = (unsigned)g.isize;
+  x.sk = (unsigned)g.sk;
+  x.c = (unsigned)i + x.sj * (unsigned)j + x.sk * (unsigned)k;
+  x.i = i; x.j = j; x.k = k;
+  return x;
+}
+
 template <int RS>
 static void step(const Grid& g, const double* Uin, double* Uout, double* work, double dt)
 {
   const MhdWork w = mhd_work_split(work, g.sv);
   const double dtdx = dt / g.dx, dtdy = dt / g.dy, dtdz = dt / g.dz;
-#define LOOP for (int k = 0; k < g.ksize; ++k) for (int j = 0; j < g.jsize; ++j) for (int i = 0; i < g.isize; ++i)
-  LOOP mhd_stage_elec(g, Uin, w.Q, w.E, i, j, k);
-  LOOP mhd_stage_trace(g, Uin, w.Q, w.E, w.S, dtdx, dtdy, dtdz, i, j, k);
-  LOOP mhd_stage_fluxes<RS>(g, w.S, w.F, i, j, k);
-  LOOP mhd_stage_emfs(g, w.S, w.EMF, i, j, k);
-  LOOP mhd_stage_update(g, Uin, w.F, w.EMF, Uout, dtdx, dtdy, dtdz, i, j, k);
+#define LOOP for (int k = 0; k < g.ksize; ++k) for (int j = 0; j < g.jsize; ++j) for (int i = 0; i < g.isize; ++i) if (MhdIdx x = idx(g, i, j, k); true)
+  LOOP mhd_stage_elec(g, Uin, w.Q, w.E, x);
+  LOOP mhd_stage_trace(g, Uin, w.Q, w.E, w.S, dtdx, dtdy, dtdz, x);
+  LOOP mhd_stage_fluxes<RS>(g, w.S, w.F, x);
+  LOOP mhd_stage_emfs(g, w.S, w.EMF, x);
+  LOOP mhd_stage_update(g, Uin, w.F, w.EMF, Uout, dtdx, dtdy, dtdz, x);
 }
 
 extern "C" {
@@ -32,11 +42,11 @@ double emul_mhd_invdt(const ek_params* p, const double* U, double* work)
   const Grid g = make_grid(*p);
   const MhdWork w = mhd_work_split(work, g.sv);
   double m = 0.0;
-  LOOP m = fmax(m, mhd_stage_prims(g, U, w.Q, i, j, k));
+  LOOP m = fmax(m, mhd_stage_prims(g, U, w.Q, x));
   return m;
 }
 
-long long emul_mhd_work_len(const ek_params* p) { return (long long)W_TOTAL * make_grid(*p).sv; }
+long long emul_mhd_work_len(const ek_params* p) { return (long long)W_TOTAL * mhd_padded_cells(make_grid(*p).sv); }
 
 // one step with a given dt on a ghost-filled Uin; Uout must be a copy of Uin (ghosts are not written)
 int emul_mhd_step(const ek_params* p, const double* Uin, double* Uout, double* work, double dt)
