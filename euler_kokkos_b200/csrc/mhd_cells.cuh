@@ -191,45 +191,76 @@ EK_HD void mhd_stage_trace(const Grid& g, const double* __restrict__ U, const do
   if (!(in_i && in_j && in_k))
     return;
 
-  // cell-centred half step
+  // cell-centred half step, accumulated direction by direction (x, then y, then z: the reference's
+  // own summation order) so that only one direction's slopes are live at a time
   const double st = g.slope_type;
   const bool use_slopes = (st == 1.0 || st == 2.0); // slope_unsplit_hydro_3d, :379,:470
   const double* __restrict__ Q0 = Q + tile_off<8>(c);
-  const double* __restrict__ Qxm = Q + tile_off<8>(c - 1);
-  const double* __restrict__ Qxp = Q + tile_off<8>(c + 1);
-  const double* __restrict__ Qym = Q + tile_off<8>(c - x.sj);
-  const double* __restrict__ Qyp = Q + tile_off<8>(c + x.sj);
-  const double* __restrict__ Qzm = Q + tile_off<8>(c - x.sk);
-  const double* __restrict__ Qzp = Q + tile_off<8>(c + x.sk);
-  double q[8], dx_[8], dy_[8], dz_[8];
+  double q[8];
 #pragma unroll
-  for (int v = 0; v < 8; ++v) {
-    const double qc = Q0[TL * v];
-    q[v] = qc;
-    // halved limited slopes (the reference halves them first thing in the trace, :765-806); the
-    // normal-field slopes (dAx, dBy, dCz) come from the face values instead (:825-827)
-    dx_[v] = (use_slopes && v != IA) ? 0.5 * mhd_slope(st, Qxm[TL * v], qc, Qxp[TL * v]) : 0.0;
-    dy_[v] = (use_slopes && v != IB) ? 0.5 * mhd_slope(st, Qym[TL * v], qc, Qyp[TL * v]) : 0.0;
-    dz_[v] = (use_slopes && v != IC) ? 0.5 * mhd_slope(st, Qzm[TL * v], qc, Qzp[TL * v]) : 0.0;
-  }
-  const double AR = UA[1], BR = UB[sj], CR = UC[sk];
+  for (int v = 0; v < 8; ++v)
+    q[v] = Q0[TL * v];
   const double r = q[ID], p = q[IP], u = q[IU], v = q[IV], w = q[IW], A = q[IA], B = q[IB], C = q[IC];
-  const double drx = dx_[ID], dpx = dx_[IP], dux = dx_[IU], dvx = dx_[IV], dwx = dx_[IW], dBx = dx_[IB], dCx = dx_[IC];
-  const double dry = dy_[ID], dpy = dy_[IP], duy = dy_[IU], dvy = dy_[IV], dwy = dy_[IW], dAy = dy_[IA], dCy = dy_[IC];
-  const double drz = dz_[ID], dpz = dz_[IP], duz = dz_[IU], dvz = dz_[IV], dwz = dz_[IW], dAz = dz_[IA], dBz = dz_[IB];
-  const double dAx = 0.5 * (AR - AL), dBy = 0.5 * (BR - BL), dCz = 0.5 * (CR - CL);
   const double ir = rcp_fast(r);
-  const double gamma = g.gamma0;
-
-  const double sr0 = (-u * drx - dux * r) * dtdx + (-v * dry - dvy * r) * dtdy + (-w * drz - dwz * r) * dtdz;
-  const double su0 = (-u * dux - (dpx + B * dBx + C * dCx) * ir) * dtdx + (-v * duy + B * dAy * ir) * dtdy + (-w * duz + C * dAz * ir) * dtdz;
-  const double sv0 = (-u * dvx + A * dBx * ir) * dtdx + (-v * dvy - (dpy + A * dAy + C * dCy) * ir) * dtdy + (-w * dvz + C * dBz * ir) * dtdz;
-  const double sw0 = (-u * dwx + A * dCx * ir) * dtdx + (-v * dwy + B * dCy * ir) * dtdy + (-w * dwz - (dpz + A * dAz + B * dBz) * ir) * dtdz;
-  const double sp0 = (-u * dpx - dux * gamma * p) * dtdx + (-v * dpy - dvy * gamma * p) * dtdy + (-w * dpz - dwz * gamma * p) * dtdz;
-  const double sA0 = (u * dBy + B * duy - v * dAy - A * dvy) * dtdy + (u * dCz + C * duz - w * dAz - A * dwz) * dtdz;
-  const double sB0 = (v * dAx + A * dvx - u * dBx - B * dux) * dtdx + (v * dCz + C * dvz - w * dBz - B * dwz) * dtdz;
-  const double sC0 = (w * dAx + A * dwx - u * dCx - C * dux) * dtdx + (w * dBy + B * dwy - v * dCy - C * dvy) * dtdy;
-
+  const double gp = g.gamma0 * p;
+  double sr0, sp0, su0, sv0, sw0, sA0, sB0, sC0;
+  {
+    const double* __restrict__ Qm = Q + tile_off<8>(c - 1);
+    const double* __restrict__ Qp = Q + tile_off<8>(c + 1);
+    double d[8];
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+      d[n] = (use_slopes && n != IA) ? 0.5 * mhd_slope(st, Qm[TL * n], q[n], Qp[TL * n]) : 0.0;
+    const double drx = d[ID], dpx = d[IP], dux = d[IU], dvx = d[IV], dwx = d[IW], dBx = d[IB], dCx = d[IC];
+    const double dAx = 0.5 * (UA[1] - AL);
+    sr0 = (-u * drx - dux * r) * dtdx;
+    su0 = (-u * dux - (dpx + B * dBx + C * dCx) * ir) * dtdx;
+    sv0 = (-u * dvx + A * dBx * ir) * dtdx;
+    sw0 = (-u * dwx + A * dCx * ir) * dtdx;
+    sp0 = (-u * dpx - dux * gp) * dtdx;
+    sB0 = (v * dAx + A * dvx - u * dBx - B * dux) * dtdx;
+    sC0 = (w * dAx + A * dwx - u * dCx - C * dux) * dtdx;
+    Sc[TL * (SX + 0)] = drx; Sc[TL * (SX + 1)] = dpx; Sc[TL * (SX + 2)] = dux; Sc[TL * (SX + 3)] = dvx; Sc[TL * (SX + 4)] = dwx;
+    Sc[TL * (SX + 5)] = dBx; Sc[TL * (SX + 6)] = dCx;
+  }
+  {
+    const double* __restrict__ Qm = Q + tile_off<8>(c - x.sj);
+    const double* __restrict__ Qp = Q + tile_off<8>(c + x.sj);
+    double d[8];
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+      d[n] = (use_slopes && n != IB) ? 0.5 * mhd_slope(st, Qm[TL * n], q[n], Qp[TL * n]) : 0.0;
+    const double dry = d[ID], dpy = d[IP], duy = d[IU], dvy = d[IV], dwy = d[IW], dAy = d[IA], dCy = d[IC];
+    const double dBy = 0.5 * (UB[sj] - BL);
+    sr0 += (-v * dry - dvy * r) * dtdy;
+    su0 += (-v * duy + B * dAy * ir) * dtdy;
+    sv0 += (-v * dvy - (dpy + A * dAy + C * dCy) * ir) * dtdy;
+    sw0 += (-v * dwy + B * dCy * ir) * dtdy;
+    sp0 += (-v * dpy - dvy * gp) * dtdy;
+    sA0 = (u * dBy + B * duy - v * dAy - A * dvy) * dtdy;
+    sC0 += (w * dBy + B * dwy - v * dCy - C * dvy) * dtdy;
+    Sc[TL * (SY + 0)] = dry; Sc[TL * (SY + 1)] = dpy; Sc[TL * (SY + 2)] = duy; Sc[TL * (SY + 3)] = dvy; Sc[TL * (SY + 4)] = dwy;
+    Sc[TL * (SY + 5)] = dAy; Sc[TL * (SY + 6)] = dCy;
+  }
+  {
+    const double* __restrict__ Qm = Q + tile_off<8>(c - x.sk);
+    const double* __restrict__ Qp = Q + tile_off<8>(c + x.sk);
+    double d[8];
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+      d[n] = (use_slopes && n != IC) ? 0.5 * mhd_slope(st, Qm[TL * n], q[n], Qp[TL * n]) : 0.0;
+    const double drz = d[ID], dpz = d[IP], duz = d[IU], dvz = d[IV], dwz = d[IW], dAz = d[IA], dBz = d[IB];
+    const double dCz = 0.5 * (UC[sk] - CL);
+    sr0 += (-w * drz - dwz * r) * dtdz;
+    su0 += (-w * duz + C * dAz * ir) * dtdz;
+    sv0 += (-w * dvz + C * dBz * ir) * dtdz;
+    sw0 += (-w * dwz - (dpz + A * dAz + B * dBz) * ir) * dtdz;
+    sp0 += (-w * dpz - dwz * gp) * dtdz;
+    sA0 += (u * dCz + C * duz - w * dAz - A * dwz) * dtdz;
+    sB0 += (v * dCz + C * dvz - w * dBz - B * dwz) * dtdz;
+    Sc[TL * (SZ + 0)] = drz; Sc[TL * (SZ + 1)] = dpz; Sc[TL * (SZ + 2)] = duz; Sc[TL * (SZ + 3)] = dvz; Sc[TL * (SZ + 4)] = dwz;
+    Sc[TL * (SZ + 5)] = dAz; Sc[TL * (SZ + 6)] = dBz;
+  }
   Sc[TL * (SC + ID)] = r + sr0;
   Sc[TL * (SC + IP)] = p + sp0;
   Sc[TL * (SC + IU)] = u + su0;
@@ -238,12 +269,6 @@ EK_HD void mhd_stage_trace(const Grid& g, const double* __restrict__ U, const do
   Sc[TL * (SC + IA)] = A + sA0;
   Sc[TL * (SC + IB)] = B + sB0;
   Sc[TL * (SC + IC)] = C + sC0;
-  Sc[TL * (SX + 0)] = drx; Sc[TL * (SX + 1)] = dpx; Sc[TL * (SX + 2)] = dux; Sc[TL * (SX + 3)] = dvx; Sc[TL * (SX + 4)] = dwx;
-  Sc[TL * (SX + 5)] = dBx; Sc[TL * (SX + 6)] = dCx;
-  Sc[TL * (SY + 0)] = dry; Sc[TL * (SY + 1)] = dpy; Sc[TL * (SY + 2)] = duy; Sc[TL * (SY + 3)] = dvy; Sc[TL * (SY + 4)] = dwy;
-  Sc[TL * (SY + 5)] = dAy; Sc[TL * (SY + 6)] = dCy;
-  Sc[TL * (SZ + 0)] = drz; Sc[TL * (SZ + 1)] = dpz; Sc[TL * (SZ + 2)] = duz; Sc[TL * (SZ + 3)] = dvz; Sc[TL * (SZ + 4)] = dwz;
-  Sc[TL * (SZ + 5)] = dAz; Sc[TL * (SZ + 6)] = dBz;
 }
 
 // ---- stage R ------------------------------------------------------------------------------------

@@ -99,6 +99,21 @@ __global__ void __launch_bounds__(128) mhd_emf_kernel(const MhdArgs a)
     mhd_stage_emfs(a.g, w.S, w.EMF, x);
 }
 
+// stage R in one pass: the three face fluxes, then the three edge EMFs of the same cell (the S
+// lines of the cell and its neighbours are read once from HBM and served from L1/L2 the second time)
+template <int RS>
+__global__ void __launch_bounds__(128, 4) mhd_faces_edges_kernel(const MhdArgs a)
+{
+  if (a.ts->finished)
+    return;
+  const MhdWork w = mhd_work_split(a.work, a.g.sv);
+  MhdIdx x;
+  if (mhd_cell_of_thread(a.g, x)) {
+    mhd_stage_fluxes<RS>(a.g, w.S, w.F, x);
+    mhd_stage_emfs(a.g, w.S, w.EMF, x);
+  }
+}
+
 __global__ void __launch_bounds__(256) mhd_update_kernel(const MhdArgs a)
 {
   if (a.ts->finished)

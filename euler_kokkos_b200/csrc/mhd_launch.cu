@@ -1,4 +1,5 @@
 // Host-side dispatch of the CT-MHD step (MHD_Muscl_3D).
+#include <cstdlib>
 #include "ek_internal.h"
 #include "mhd_kernels.cuh"
 
@@ -45,10 +46,16 @@ static cudaError_t launch_step(Ctx& c, const double* Uin, double* Uout)
   c.mhd_prims_of = nullptr;
   mhd_elec_kernel<<<blocks(c.g, 256), 256, 0, c.stream>>>(a);
   mhd_trace_kernel<<<blocks(c.g, 256), 256, 0, c.stream>>>(a);
-  mhd_flux_kernel<RS><<<blocks(c.g, 128), 128, 0, c.stream>>>(a);
-  mhd_emf_kernel<<<blocks(c.g, 128), 128, 0, c.stream>>>(a);
+  static const int fuse_r = getenv("EK_MHD_FUSE_R") ? atoi(getenv("EK_MHD_FUSE_R")) : 1; // tuning switch (default: fused)
+  if (fuse_r) {
+    mhd_faces_edges_kernel<RS><<<blocks(c.g, 128), 128, 0, c.stream>>>(a);
+    c.launches += 4;
+  } else {
+    mhd_flux_kernel<RS><<<blocks(c.g, 128), 128, 0, c.stream>>>(a);
+    mhd_emf_kernel<<<blocks(c.g, 128), 128, 0, c.stream>>>(a);
+    c.launches += 5;
+  }
   mhd_update_kernel<<<blocks(c.g, 256), 256, 0, c.stream>>>(a);
-  c.launches += 5;
   return cudaGetLastError();
 }
 
