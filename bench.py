@@ -24,6 +24,7 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+os.environ.setdefault("EKH_QUIET", "1")  # stdout carries exactly one JSON line
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
@@ -239,7 +240,7 @@ def run_ours(args):
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(args)
-        print(json.dumps(line))
+        emit(line)
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
@@ -312,7 +313,29 @@ def run_reference_arm(args):
         "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": threads, "kind": "reference", "sample": desc},
         "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """Everything that libraries print to fd 1 (NCCL's version line, C++ banners) goes to stderr; the
+    ONE JSON line is written to the real stdout by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -327,6 +350,7 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    protect_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -47,6 +47,27 @@ struct Grid {
 EK_HD double dmax(double a, double b) { return (a > b) ? a : b; }
 EK_HD double dmin(double a, double b) { return (a < b) ? a : b; }
 
+// Limited slope of the reference (slope_unsplit_hydro_{2d,3d}_scalar, HydroBaseFunctor3D.h:413-461;
+// same formula in MHDBaseFunctor3D.h:262-337 and for the face field in :563-668):
+//   dlft = st*(q-qm), drgt = st*(qp-q), dcen = (qp-qm)/2, dlim = (dlft*drgt <= 0) ? 0 : min(|dlft|,|drgt|),
+//   slope = sign(dcen) * min(dlim, |dcen|)
+// evaluated with 8 FP64-pipe operations: "dlft*drgt <= 0" is decided on the sign bits (a zero factor
+// makes the min zero anyway) and sign(dcen) is transplanted with copysign (when the signs of dlft and
+// drgt agree, dcen has that sign too; the sign of a zero result is immaterial).
+EK_HD double limited_slope_ref(double st, double qm, double q, double qp)
+{
+  const double dl = st * (q - qm);
+  const double dr = st * (qp - q);
+  const double dc = 0.5 * (qp - qm);
+  const double m = dmin(dmin(fabs(dl), fabs(dr)), fabs(dc));
+#ifdef __CUDA_ARCH__
+  const bool opposite = (__double2hiint(dl) ^ __double2hiint(dr)) < 0;
+#else
+  const bool opposite = std::signbit(dl) != std::signbit(dr);
+#endif
+  return opposite ? 0.0 : copysign(m, dc);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Division / square root.  EK_PRECISE_MATH=1 uses IEEE-rounded '/' and sqrt() everywhere (parity
 // bisecting build); the default uses MUFU seeds + FMA Newton steps without the IEEE special-case

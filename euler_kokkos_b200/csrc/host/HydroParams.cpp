@@ -187,7 +187,8 @@ void HydroParams::setup_decomposition(const ConfigMap& configMap, const Parallel
   dx = (xmax - xmin) / (nx * mx);
   dy = (ymax - ymin) / (ny * my);
   dz = (zmax - zmin) / (nz * mz);
-  if (myRank == 0 && nProcs > 1) {
+  // the driver's banner (HydroParams.cpp:305-318 of the reference); library users (bench, tests) silence it
+  if (myRank == 0 && nProcs > 1 && !std::getenv("EKH_QUIET")) {
     std::cout << "We are about to start simulation with the following characteristics\n";
     std::cout << "Global resolution : " << nx * mx << " x " << ny * my << " x " << nz * mz << "\n";
     std::cout << "Local  resolution : " << nx << " x " << ny << " x " << nz << "\n";

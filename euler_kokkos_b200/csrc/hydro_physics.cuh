@@ -75,13 +75,7 @@ __device__ __forceinline__ double hydro_cell_invdt(const Grid& g, const double* 
 // ---- limited slope ---------------------------------------------------------------------------
 __device__ __forceinline__ double limited_slope(double st, double qm, double q, double qp)
 {
-  const double dl = st * (q - qm);
-  const double dr = st * (qp - q);
-  const double dc = 0.5 * (qp - qm);
-  double lim = dmin(fabs(dl), fabs(dr));
-  lim = (dl * dr <= 0.0) ? 0.0 : lim;
-  const double m = dmin(lim, fabs(dc));
-  return (dc >= 0.0) ? m : -m;
+  return limited_slope_ref(st, qm, q, qp);
 }
 
 // ---- Hancock predictor: source terms of one cell ---------------------------------------------

@@ -40,13 +40,7 @@ struct MhdCorner {
 // for the face-centred field in slope_unsplit_mhd_3d, :563-668)
 EK_HD double mhd_slope(double st, double qm, double q, double qp)
 {
-  const double dl = st * (q - qm);
-  const double dr = st * (qp - q);
-  const double dc = 0.5 * (qp - qm);
-  double lim = dmin(fabs(dl), fabs(dr));
-  lim = (dl * dr <= 0.0) ? 0.0 : lim;
-  const double m = dmin(lim, fabs(dc));
-  return (dc >= 0.0) ? m : -m;
+  return limited_slope_ref(st, qm, q, qp);
 }
 
 // ---- conservative -> primitive (cell-centred B = mean of the two faces) -----------------------
