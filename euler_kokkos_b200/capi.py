@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libek_b200.so")
+LIB_PATH = os.environ.get("EK_B200_LIB") or os.path.join(_HERE, "lib", "libek_b200.so")  # env override: kernel-tuning builds
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

@@ -8,10 +8,14 @@
 //
 // Tiling ("2.5-D z-march"): a CTA owns a TX x TY column of interior cells (TX = 28 so that the
 // tile + 2-cell halo is exactly one 32-lane warp wide; one warp per tile row, TY+4 warps) and
-// marches along z over a chunk of planes.  Per plane the z-neighbours of a cell live in the
-// registers of the thread that owns the column; x/y neighbours are exchanged through shared memory.
-// Every Riemann problem is solved once per face (by the thread of the upper cell), every slope and
-// trace once per cell; only the 1-cell ring around the tile is computed redundantly.
+// marches along z over a chunk of planes.  All plane-to-plane state lives in shared memory:
+//   q[3]   ring of primitive planes p-1, p, p+1 (x/y neighbours AND the thread's own z neighbours)
+//   mz[2]  ZMAX-face state of the previous / current plane (own slot only)
+//   part   running update U + fx - fx' + fy - fy' + fz of the previous plane (own slot only)
+// which keeps the register file free for the three Riemann problems of a cell (lower x, y and z face),
+// solved in lock step so that their serial FP64 chains interleave (riemann_hllc_n).  Every Riemann
+// problem is solved once per face, every slope and trace once per cell; only the 1-cell ring around
+// the tile is computed redundantly.  Two barriers per plane.
 #pragma once
 #include "hydro_physics.cuh"
 
@@ -24,12 +28,15 @@ struct HydroSmem {
   static constexpr int NV = HydroTraits<DIM>::NV;
   static constexpr int ROWS = TY + 4;
   static constexpr int PLANE = ROWS * 32; // doubles per variable
-  double q[NV * PLANE];   // primitives of the current plane
-  double mx[NV * PLANE];  // state on the XMAX face of each cell (left state of face i+1)
-  double my[NV * PLANE];  // state on the YMAX face of each cell
-  double fx[NV * PLANE];  // flux*dt/dx through the lower x face of each cell
-  double fy[NV * PLANE];  // flux*dt/dy through the lower y face of each cell
-  double red[ROWS];       // per-warp invDt maxima
+  static constexpr int NRING = (DIM == 3) ? 3 : 1;
+  double q[NRING][NV * PLANE];       // primitives: ring of planes
+  double mx[NV * PLANE];             // state on the XMAX face of each cell (left state of face i+1)
+  double my[NV * PLANE];             // state on the YMAX face of each cell
+  double fx[NV * PLANE];             // flux*dt/dx through the lower x face of each cell
+  double fy[NV * PLANE];             // flux*dt/dy through the lower y face of each cell
+  double mz[(DIM == 3) ? 2 : 1][NV * PLANE]; // ZMAX-face state, double buffered by plane parity (3-D)
+  double part[1][NV * PLANE];                // partial update of the previous plane (3-D)
+  double red[ROWS];                  // per-warp invDt maxima
 };
 
 struct HydroArgs {
@@ -54,7 +61,7 @@ __global__ void __launch_bounds__(32 * (TY + 4), 1) hydro_step_kernel(const Hydr
   if (a.ts->finished)
     return;
   const double dt = a.ts->dt;
-  const double dtd[3] = { dt / g.dx, dt / g.dy, (DIM == 3) ? dt / g.dz : 0.0 };
+  const double dtd[3] = { dt * g.invdx, dt * g.invdy, (DIM == 3) ? dt * g.invdz : 0.0 };
 
   const int lane = threadIdx.x, row = threadIdx.y;
   const int xg = g.gw + blockIdx.x * HTX + lane - 2; // ghosted coordinates of this thread's column
@@ -70,22 +77,22 @@ __global__ void __launch_bounds__(32 * (TY + 4), 1) hydro_step_kernel(const Hydr
   const bool do_fx = inb && lane >= 2 && lane <= 30 && xg <= g.nx + g.gw && in_y; // lower x faces
   const bool do_fy = inb && in_x && row >= 2 && row <= TY + 2 && yg <= g.ny + g.gw;
   const bool do_cell = in_x && in_y;
+  const bool row_flux = row >= 2 && row <= TY + 2; // warp-uniform: this row solves Riemann problems
 
   const long long col = (long long)xg + g.sj * (long long)yg;
   const double* __restrict__ Uin = a.Uin;
 
-  auto load_prims = [&](int k, double* q) {
-    if (inb) {
-      double u[NV], rd;
+  auto prims_to_ring = [&](const double* u, int slot) {
+    double q[NV], rd;
+    hydro_cons_to_prim<DIM>(g, u, q, rd);
 #pragma unroll
-      for (int v = 0; v < NV; ++v)
-        u[v] = __ldg(Uin + col + g.sk * k + g.sv * v);
-      hydro_cons_to_prim<DIM>(g, u, q, rd);
-    } else {
+    for (int v = 0; v < NV; ++v)
+      sm.q[slot][v * PLANE + so] = q[v];
+  };
+  auto load_u = [&](int k, double* u) {
 #pragma unroll
-      for (int v = 0; v < NV; ++v)
-        q[v] = 1.0;
-    }
+    for (int v = 0; v < NV; ++v)
+      u[v] = inb ? __ldg(Uin + col + g.sk * k + g.sv * v) : 1.0;
   };
 
   int kbeg = 0, kend = 1;
@@ -93,56 +100,52 @@ __global__ void __launch_bounds__(32 * (TY + 4), 1) hydro_step_kernel(const Hydr
     kbeg = g.gw + blockIdx.z * a.zchunk;
     kend = min(kbeg + a.zchunk, g.nz + g.gw);
   }
-
-  double qprev[NV], qcur[NV], qnext[NV]; // z pipeline of primitives (3-D)
-  double mzprev[NV];                     // ZMAX-face state of the previous plane
-  double part[NV];                       // U + fx - fx' + fy - fy' + fz of the previous plane
   double invdt = 0.0;
 
-  if constexpr (DIM == 3) {
-    load_prims(kbeg - 2, qprev);
-    load_prims(kbeg - 1, qcur);
-    load_prims(kbeg, qnext);
-  } else {
-    load_prims(0, qcur);
+  // prologue: primitives of the first planes into the ring (slot of plane k = (k - kbeg + 2) % 3)
+  {
+    double u[NV];
+    if constexpr (DIM == 3) {
+      load_u(kbeg - 2, u);
+      prims_to_ring(u, 0);
+      load_u(kbeg - 1, u);
+      prims_to_ring(u, 1);
+      load_u(kbeg, u);
+      prims_to_ring(u, 2);
+    } else {
+      load_u(0, u);
+      prims_to_ring(u, 0);
+    }
   }
-#pragma unroll
-  for (int v = 0; v < NV; ++v) {
-    mzprev[v] = 1.0;
-    part[v] = 0.0;
-  }
+  __syncthreads();
 
   const int pbeg = (DIM == 3) ? kbeg - 1 : 0;
   const int pend = (DIM == 3) ? kend : 0; // inclusive
+  int s0 = (DIM == 3) ? 1 : 0;            // ring slot of plane p
 
   for (int p = pbeg; p <= pend; ++p) {
-    // -- prefetch the conserved state two planes ahead (consumed at the bottom of the loop)
+    const int sm1 = (s0 == 0) ? 2 : s0 - 1, sp1 = (s0 == 2) ? 0 : s0 + 1;
+    const int zb = p & 1; // mz buffer written for plane p; plane p-1 sits in zb^1
+    // -- prefetch the conserved state two planes ahead (converted at the bottom of the loop)
     double unext[NV];
-    const bool have_next = (DIM == 3) && (p + 2 <= kend + 1) && inb;
-    if (have_next) {
-#pragma unroll
-      for (int v = 0; v < NV; ++v)
-        unext[v] = __ldg(Uin + col + g.sk * (p + 2) + g.sv * v);
-    }
-
-    // -- publish primitives of plane p
-#pragma unroll
-    for (int v = 0; v < NV; ++v)
-      sm.q[v * PLANE + so] = qcur[v];
-    __syncthreads();
+    const bool have_next = (DIM == 3) && (p + 2 <= kend + 1);
+    if (have_next)
+      load_u(p + 2, unext);
 
     // -- slopes + Hancock trace of this cell
-    double px[NV], py[NV], pz[NV], mz[NV]; // states on the XMIN, YMIN, ZMIN, ZMAX faces
+    double lo[3][5]; // states on the XMIN, YMIN, ZMIN faces (right states of the lower faces)
     if (do_trace) {
-      double dq[3][5];
+      double qc[NV], dq[3][5];
       const double st = g.slope_type;
+      const double* __restrict__ q0 = sm.q[(DIM == 3) ? s0 : 0];
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
-        const double qc = qcur[v];
-        dq[0][v] = limited_slope(st, sm.q[v * PLANE + so - 1], qc, sm.q[v * PLANE + so + 1]);
-        dq[1][v] = limited_slope(st, sm.q[v * PLANE + so - 32], qc, sm.q[v * PLANE + so + 32]);
+        const double c = q0[v * PLANE + so];
+        qc[v] = c;
+        dq[0][v] = limited_slope(st, q0[v * PLANE + so - 1], c, q0[v * PLANE + so + 1]);
+        dq[1][v] = limited_slope(st, q0[v * PLANE + so - 32], c, q0[v * PLANE + so + 32]);
         if constexpr (DIM == 3)
-          dq[2][v] = limited_slope(st, qprev[v], qc, qnext[v]);
+          dq[2][v] = limited_slope(st, sm.q[sm1][v * PLANE + so], c, sm.q[sp1][v * PLANE + so]);
       }
       if (st == 0.0) { // slope_type 0: first-order (HydroBaseFunctor3D.h:498-520)
 #pragma unroll
@@ -152,7 +155,7 @@ __global__ void __launch_bounds__(32 * (TY + 4), 1) hydro_step_kernel(const Hydr
             dq[d][v] = 0.0;
       }
       double s[NV];
-      hydro_sources<DIM>(g, qcur, dq, s);
+      hydro_sources<DIM>(g, qc, dq, s);
       double gh[3] = { 0.0, 0.0, 0.0 }; // gravity predictor 0.5*dt*g on the velocities
       if constexpr (GRAV) {
         if (g.gravity_hancock) {
@@ -166,13 +169,13 @@ __global__ void __launch_bounds__(32 * (TY + 4), 1) hydro_step_kernel(const Hydr
         const double add = (v >= IU) ? gh[v - IU] : 0.0;
         const double sx = s[v] * (dtd[0] * 0.5), sy = s[v] * (dtd[1] * 0.5);
         const double hx = 0.5 * dq[0][v], hy = 0.5 * dq[1][v];
-        px[v] = (qcur[v] - hx) + sx + add;
-        py[v] = (qcur[v] - hy) + sy + add;
-        double mxv = (qcur[v] + hx) + sx + add;
-        double myv = (qcur[v] + hy) + sy + add;
+        lo[0][v] = (qc[v] - hx) + sx + add;
+        lo[1][v] = (qc[v] - hy) + sy + add;
+        double mxv = (qc[v] + hx) + sx + add;
+        double myv = (qc[v] + hy) + sy + add;
         if (v == ID) {
-          px[v] = dmax(g.smallr, px[v]);
-          py[v] = dmax(g.smallr, py[v]);
+          lo[0][v] = dmax(g.smallr, lo[0][v]);
+          lo[1][v] = dmax(g.smallr, lo[1][v]);
           mxv = dmax(g.smallr, mxv);
           myv = dmax(g.smallr, myv);
         }
@@ -184,68 +187,76 @@ __global__ void __launch_bounds__(32 * (TY + 4), 1) hydro_step_kernel(const Hydr
           // implementationVersion 1 omits the gravity predictor on the ZMIN-face state
           // (HydroRunFunctors3D.h:1351 vs :1277-1285)
           const double addz = (g.impl_version == 1) ? 0.0 : add;
-          pz[v] = (qcur[v] - hz) + sz + addz;
-          mz[v] = (qcur[v] + hz) + sz + add;
+          lo[2][v] = (qc[v] - hz) + sz + addz;
+          double mzv = (qc[v] + hz) + sz + add;
           if (v == ID) {
-            pz[v] = dmax(g.smallr, pz[v]);
-            mz[v] = dmax(g.smallr, mz[v]);
+            lo[2][v] = dmax(g.smallr, lo[2][v]);
+            mzv = dmax(g.smallr, mzv);
           }
+          sm.mz[zb][v * PLANE + so] = mzv;
         }
       }
+    } else {
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+#pragma unroll
+        for (int v = 0; v < 5; ++v)
+          lo[d][v] = 1.0; // halo lanes ride along in the lock-step solve; their fluxes are discarded
     }
     __syncthreads();
 
-    // -- Riemann problems at the lower x / y / z faces of this cell
-    double fxl[NV], fyl[NV], fzl[NV];
+    // -- Riemann problems at the lower x / y / z faces of this cell, solved in lock step
+    double fl[3][5];
 #pragma unroll
-    for (int v = 0; v < NV; ++v)
-      fxl[v] = fyl[v] = fzl[v] = 0.0;
-    if (do_fx) {
-      double ql[NV];
+    for (int d = 0; d < 3; ++d)
 #pragma unroll
-      for (int v = 0; v < NV; ++v)
-        ql[v] = sm.mx[v * PLANE + so - 1];
-      riemann_hydro<DIM, RS>(g, ql, px, fxl);
+      for (int v = 0; v < 5; ++v)
+        fl[d][v] = 0.0;
+    if (row_flux) {
+      double ql[3][5], qr[3][5], f[3][5];
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
-        fxl[v] *= dtd[0];
-        sm.fx[v * PLANE + so] = fxl[v];
+        ql[0][v] = sm.mx[v * PLANE + so - 1];
+        ql[1][v] = sm.my[v * PLANE + so - 32];
+        qr[0][v] = lo[0][v];
+        qr[1][v] = lo[1][v];
+        if constexpr (DIM == 3) {
+          ql[2][v] = sm.mz[zb ^ 1][v * PLANE + so];
+          qr[2][v] = lo[2][v];
+        }
       }
-    }
-    if (do_fy) {
-      double ql[NV], qr[NV], f[NV];
-#pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        ql[v] = sm.my[v * PLANE + so - 32];
-        qr[v] = py[v];
+      // rotate into the face-normal frame: normal velocity first (HydroRunFunctors3D.h:597-608,692-703)
+      { double t = ql[1][IU]; ql[1][IU] = ql[1][IV]; ql[1][IV] = t; }
+      { double t = qr[1][IU]; qr[1][IU] = qr[1][IV]; qr[1][IV] = t; }
+      if constexpr (DIM == 3) {
+        { double t = ql[2][IU]; ql[2][IU] = ql[2][IW]; ql[2][IW] = t; }
+        { double t = qr[2][IU]; qr[2][IU] = qr[2][IW]; qr[2][IW] = t; }
       }
-      // rotate: normal velocity first
-      { double t = ql[IU]; ql[IU] = ql[IV]; ql[IV] = t; }
-      { double t = qr[IU]; qr[IU] = qr[IV]; qr[IV] = t; }
-      riemann_hydro<DIM, RS>(g, ql, qr, f);
-      { double t = f[IU]; f[IU] = f[IV]; f[IV] = t; }
-#pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        fyl[v] = f[v] * dtd[1];
-        sm.fy[v * PLANE + so] = fyl[v];
+      riemann_hydro_n<DIM, RS, DIM>(g, ql, qr, f);
+      { double t = f[1][IU]; f[1][IU] = f[1][IV]; f[1][IV] = t; }
+      if constexpr (DIM == 3) {
+        double t = f[2][IU]; f[2][IU] = f[2][IW]; f[2][IW] = t;
       }
-    }
-    if constexpr (DIM == 3) {
-      if (do_cell) { // face between plane p-1 and p (p-1 >= kbeg-1 has been traced, except at p == pbeg)
-        if (p > pbeg) {
-          double ql[NV], qr[NV], f[NV];
+      if (do_fx) {
 #pragma unroll
-          for (int v = 0; v < NV; ++v) {
-            ql[v] = mzprev[v];
-            qr[v] = pz[v];
-          }
-          { double t = ql[IU]; ql[IU] = ql[IW]; ql[IW] = t; }
-          { double t = qr[IU]; qr[IU] = qr[IW]; qr[IW] = t; }
-          riemann_hydro<DIM, RS>(g, ql, qr, f);
-          { double t = f[IU]; f[IU] = f[IW]; f[IW] = t; }
+        for (int v = 0; v < NV; ++v) {
+          fl[0][v] = f[0][v] * dtd[0];
+          sm.fx[v * PLANE + so] = fl[0][v];
+        }
+      }
+      if (do_fy) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          fl[1][v] = f[1][v] * dtd[1];
+          sm.fy[v * PLANE + so] = fl[1][v];
+        }
+      }
+      if constexpr (DIM == 3) {
+        // face between plane p-1 and p (plane p-1 has been traced except at p == pbeg)
+        if (do_cell && p > pbeg) {
 #pragma unroll
           for (int v = 0; v < NV; ++v)
-            fzl[v] = f[v] * dtd[2];
+            fl[2][v] = f[2][v] * dtd[2];
         }
       }
     }
@@ -258,7 +269,7 @@ __global__ void __launch_bounds__(32 * (TY + 4), 1) hydro_step_kernel(const Hydr
           double un[NV];
 #pragma unroll
           for (int v = 0; v < NV; ++v)
-            un[v] = part[v] - fzl[v];
+            un[v] = sm.part[0][v * PLANE + so] - fl[2][v];
           const long long o = col + g.sk * (p - 1);
           double gv[3] = { 0.0, 0.0, 0.0 };
           if constexpr (GRAV) {
@@ -285,12 +296,12 @@ __global__ void __launch_bounds__(32 * (TY + 4), 1) hydro_step_kernel(const Hydr
 #pragma unroll
           for (int v = 0; v < NV; ++v) {
             double u = __ldg(Uin + o + g.sv * v);
-            u += fxl[v];
+            u += fl[0][v];
             u -= sm.fx[v * PLANE + so + 1];
-            u += fyl[v];
+            u += fl[1][v];
             u -= sm.fy[v * PLANE + so + 32];
-            u += fzl[v];
-            part[v] = u;
+            u += fl[2][v];
+            sm.part[0][v * PLANE + so] = u;
           }
         }
       } else {
@@ -298,9 +309,9 @@ __global__ void __launch_bounds__(32 * (TY + 4), 1) hydro_step_kernel(const Hydr
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
           double u = __ldg(Uin + col + g.sv * v);
-          u += fxl[v];
+          u += fl[0][v];
           u -= sm.fx[v * PLANE + so + 1];
-          u += fyl[v];
+          u += fl[1][v];
           u -= sm.fy[v * PLANE + so + 32];
           un[v] = u;
         }
@@ -326,18 +337,13 @@ __global__ void __launch_bounds__(32 * (TY + 4), 1) hydro_step_kernel(const Hydr
       }
     }
 
-    // -- rotate the z pipeline
+    // -- primitives of plane p+2 replace plane p-1 in the ring (own slot: this thread is the only
+    //    reader of its plane p-1 entry, and it is done with it); visible to the neighbours two
+    //    barriers before they read it as plane "p" of iteration p+2
     if constexpr (DIM == 3) {
-#pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        qprev[v] = qcur[v];
-        qcur[v] = qnext[v];
-        mzprev[v] = mz[v];
-      }
-      if (have_next) {
-        double rd;
-        hydro_cons_to_prim<DIM>(g, unext, qnext, rd);
-      }
+      if (have_next)
+        prims_to_ring(unext, sm1);
+      s0 = sp1;
     }
   }
 

@@ -324,4 +324,106 @@ __device__ __forceinline__ void riemann_hydro(const Grid& g, const double* __res
     riemann_hll<DIM>(g, ql, qr, flux);
 }
 
+// N independent HLLC problems advanced in lock step (statement by statement) so that the FP64
+// dependency chains of the N faces interleave: the solver is a long serial chain (two reciprocal
+// Newton sequences and a square root), and a CTA only has 4 warps per scheduler to hide it.
+template <int DIM, int N>
+__device__ __forceinline__ void riemann_hllc_n(const Grid& g, const double (*ql)[5], const double (*qr)[5], double (*flux)[5])
+{
+  const double entho = g.entho;
+  const double sc2 = g.smallc * g.smallc;
+  double rl[N], pl[N], rr[N], pr[N], etotl[N], etotr[N], cmax[N], SL[N], SR[N], ustar[N], pstar[N];
+#pragma unroll
+  for (int n = 0; n < N; ++n) {
+    rl[n] = dmax(ql[n][ID], g.smallr);
+    pl[n] = dmax(ql[n][IP], rl[n] * g.smallp);
+    rr[n] = dmax(qr[n][ID], g.smallr);
+    pr[n] = dmax(qr[n][IP], rr[n] * g.smallp);
+  }
+#pragma unroll
+  for (int n = 0; n < N; ++n) {
+    double el = 0.5 * rl[n] * ql[n][IU] * ql[n][IU];
+    el += 0.5 * rl[n] * ql[n][IV] * ql[n][IV];
+    double er = 0.5 * rr[n] * qr[n][IU] * qr[n][IU];
+    er += 0.5 * rr[n] * qr[n][IV] * qr[n][IV];
+    if constexpr (DIM == 3) {
+      el += 0.5 * rl[n] * ql[n][IW] * ql[n][IW];
+      er += 0.5 * rr[n] * qr[n][IW] * qr[n][IW];
+    }
+    etotl[n] = pl[n] * entho + el;
+    etotr[n] = pr[n] * entho + er;
+  }
+  double c2l[N], c2r[N];
+#pragma unroll
+  for (int n = 0; n < N; ++n) {
+    c2l[n] = div_fast(g.gamma0 * pl[n], rl[n]);
+    c2r[n] = div_fast(g.gamma0 * pr[n], rr[n]);
+  }
+#pragma unroll
+  for (int n = 0; n < N; ++n)
+    cmax[n] = sqrt_fast(dmax(dmax(c2l[n], c2r[n]), sc2));
+  double irc[N], rcl[N], rcr[N];
+#pragma unroll
+  for (int n = 0; n < N; ++n) {
+    SL[n] = dmin(ql[n][IU], qr[n][IU]) - cmax[n];
+    SR[n] = dmax(ql[n][IU], qr[n][IU]) + cmax[n];
+    rcl[n] = rl[n] * (ql[n][IU] - SL[n]);
+    rcr[n] = rr[n] * (SR[n] - qr[n][IU]);
+  }
+#pragma unroll
+  for (int n = 0; n < N; ++n)
+    irc[n] = rcp_fast(rcr[n] + rcl[n]);
+#pragma unroll
+  for (int n = 0; n < N; ++n) {
+    const double ul = ql[n][IU], ur = qr[n][IU];
+    ustar[n] = (rcr[n] * ur + rcl[n] * ul + (pl[n] - pr[n])) * irc[n];
+    pstar[n] = (rcr[n] * pl[n] + rcl[n] * pr[n] + rcl[n] * rcr[n] * (ul - ur)) * irc[n];
+  }
+  double S[N], ro_[N], uo_[N], po_[N], eo_[N], is[N];
+#pragma unroll
+  for (int n = 0; n < N; ++n) {
+    const bool left = (ustar[n] > 0.0);
+    S[n] = left ? SL[n] : SR[n];
+    ro_[n] = left ? rl[n] : rr[n];
+    uo_[n] = left ? ql[n][IU] : qr[n][IU];
+    po_[n] = left ? pl[n] : pr[n];
+    eo_[n] = left ? etotl[n] : etotr[n];
+  }
+#pragma unroll
+  for (int n = 0; n < N; ++n)
+    is[n] = rcp_fast(S[n] - ustar[n]);
+#pragma unroll
+  for (int n = 0; n < N; ++n) {
+    const double rstar = ro_[n] * (S[n] - uo_[n]) * is[n];
+    const double estar = ((S[n] - uo_[n]) * eo_[n] - po_[n] * uo_[n] + pstar[n] * ustar[n]) * is[n];
+    // the state sampled at x/t = 0: upwind state if the fan does not contain 0, else the star state
+    const bool sup_l = SL[n] > 0.0;
+    const bool sup_r = !sup_l && !(ustar[n] > 0.0) && !(SR[n] > 0.0);
+    const double ro = sup_l ? rl[n] : sup_r ? rr[n] : rstar;
+    const double uo = sup_l ? ql[n][IU] : sup_r ? qr[n][IU] : ustar[n];
+    const double po = sup_l ? pl[n] : sup_r ? pr[n] : pstar[n];
+    const double eo = sup_l ? etotl[n] : sup_r ? etotr[n] : estar;
+    const double fm = ro * uo;
+    flux[n][ID] = fm;
+    flux[n][IU] = fm * uo + po;
+    flux[n][IP] = (eo + po) * uo;
+    const bool up = fm > 0.0;
+    flux[n][IV] = fm * (up ? ql[n][IV] : qr[n][IV]);
+    if constexpr (DIM == 3)
+      flux[n][IW] = fm * (up ? ql[n][IW] : qr[n][IW]);
+  }
+}
+
+template <int DIM, int RS, int N>
+__device__ __forceinline__ void riemann_hydro_n(const Grid& g, const double (*ql)[5], const double (*qr)[5], double (*flux)[5])
+{
+  if constexpr (RS == RIEMANN_HLLC) {
+    riemann_hllc_n<DIM, N>(g, ql, qr, flux);
+  } else {
+#pragma unroll
+    for (int n = 0; n < N; ++n)
+      riemann_hydro<DIM, RS>(g, ql[n], qr[n], flux[n]);
+  }
+}
+
 } // namespace ek
