@@ -194,7 +194,7 @@ def run_ours(args):
     # ---- end-to-end leg through the public C ABI with HOST buffers --------------------------------
     # one job = upload the initial state from pinned host memory, K host-driven steps exactly like the
     # reference's main loop (dt comes back to the host every step), download the final state.
-    out_pinned = torch.empty_like(pinned)
+    out_pinned = torch.empty(pinned.numel(), dtype=torch.float64, pin_memory=True)  # empty_like would not be pinned
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(stream):

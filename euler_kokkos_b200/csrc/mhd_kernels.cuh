@@ -4,6 +4,10 @@
 #pragma once
 #include "mhd_cells.cuh"
 
+#ifndef EK_MHD_TRACE_PREFETCH
+#define EK_MHD_TRACE_PREFETCH 1
+#endif
+
 namespace ek {
 
 struct MhdArgs {
@@ -67,15 +71,32 @@ __global__ void __launch_bounds__(256) mhd_elec_kernel(const MhdArgs a)
     mhd_stage_elec(a.g, a.Uin, w.Q, w.E, x);
 }
 
-__global__ void __launch_bounds__(256) mhd_trace_kernel(const MhdArgs a)
+#ifndef EK_MHD_TRACE_MINB
+#define EK_MHD_TRACE_MINB 3
+#endif
+__global__ void __launch_bounds__(256, EK_MHD_TRACE_MINB) mhd_trace_kernel(const MhdArgs a)
 {
   if (a.ts->finished)
     return;
   const MhdWork w = mhd_work_split(a.work, a.g.sv);
   const double dt = a.ts->dt;
   MhdIdx x;
-  if (mhd_cell_of_thread(a.g, x))
+  if (mhd_cell_of_thread(a.g, x)) {
+#if EK_MHD_TRACE_PREFETCH
+    // the stage walks x, then y, then z: pull the y/z neighbour lines of Q towards L2 while the x
+    // part waits on DRAM (the kernel is latency bound: ~80 independent loads per cell, 80 registers)
+    if (x.i >= 2 && x.j >= 2 && x.k >= 2 && x.i <= a.g.isize - 3 && x.j <= a.g.jsize - 3 && x.k <= a.g.ksize - 3) {
+      const double* qn[4] = { w.Q + tile_off<8>(x.c - x.sj), w.Q + tile_off<8>(x.c + x.sj), w.Q + tile_off<8>(x.c - x.sk),
+                              w.Q + tile_off<8>(x.c + x.sk) };
+#pragma unroll
+      for (int n = 0; n < 4; ++n)
+#pragma unroll
+        for (int v = 0; v < 8; ++v)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(qn[n] + TL * v));
+    }
+#endif
     mhd_stage_trace(a.g, a.Uin, w.Q, w.E, w.S, dt / a.g.dx, dt / a.g.dy, dt / a.g.dz, x);
+  }
 }
 
 template <int RS>
