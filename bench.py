@@ -28,7 +28,7 @@ os.environ.setdefault("EKH_QUIET", "1")  # stdout carries exactly one JSON line
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-ALGO_BYTES = {"hydro2d": 64, "hydro3d": 80, "hydro3d_grav": 104, "mhd": 128}
+ALGO_BYTES = {"hydro2d": 64, "hydro3d": 80, "hydro3d_grav": 104, "mhd": 128, "mhd2d": 128}
 
 WORKLOADS = {
     # name: (ini file in euler_kokkos_b200/settings, solver family, default n)
@@ -37,6 +37,7 @@ WORKLOADS = {
     "ot3d": dict(ini="test_mhd_orszag_tang_3D.ini", fam="mhd", n=512, cubic_box=False),
     "rt3d": dict(ini="test_rayleigh_taylor_3d.ini", fam="hydro3d_grav", n=512, cubic_box=False),
     "implode2d": dict(ini="test_implode_2D.ini", fam="hydro2d", n=None, cubic_box=False),
+    "ot2d": dict(ini="test_mhd_orszag_tang_2D.ini", fam="mhd2d", n=8192, cubic_box=False),
 }
 
 
@@ -280,8 +281,8 @@ def reference_sample(args, n_sample, nsteps, threads=None):
 
 def cpu_baseline(args):
     w = WORKLOADS[args.workload]
-    n_sample = {"hydro3d": 160, "hydro3d_grav": 160, "mhd": 96, "hydro2d": None}[w["fam"]]
-    nsteps = {"hydro3d": 6, "hydro3d_grav": 6, "mhd": 4, "hydro2d": 40}[w["fam"]]
+    n_sample = {"hydro3d": 160, "hydro3d_grav": 160, "mhd": 96, "hydro2d": None, "mhd2d": 1024}[w["fam"]]
+    nsteps = {"hydro3d": 6, "hydro3d_grav": 6, "mhd": 4, "hydro2d": 40, "mhd2d": 10}[w["fam"]]
     try:
         v, desc, threads = reference_sample(args, n_sample, nsteps)
         return {"value": v, "unit": "cell-updates/s", "cores": threads, "kind": "reference", "sample": desc}
@@ -294,8 +295,8 @@ def run_reference_arm(args):
     if rank != 0:
         return
     w = WORKLOADS[args.workload]
-    n_sample = {"hydro3d": 128, "hydro3d_grav": 128, "mhd": 80, "hydro2d": None}[w["fam"]]
-    nsteps = {"hydro3d": 3, "hydro3d_grav": 3, "mhd": 2, "hydro2d": 20}[w["fam"]]
+    n_sample = {"hydro3d": 128, "hydro3d_grav": 128, "mhd": 80, "hydro2d": None, "mhd2d": 768}[w["fam"]]
+    nsteps = {"hydro3d": 3, "hydro3d_grav": 3, "mhd": 2, "hydro2d": 20, "mhd2d": 5}[w["fam"]]
     vals, desc, threads = [], "", 0
     t_all = time.time()
     for i in range(args.warmup + args.steps):

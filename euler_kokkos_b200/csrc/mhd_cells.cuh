@@ -275,7 +275,8 @@ EK_HD void mhd_stage_trace(const Grid& g, const double* __restrict__ U, const do
 // one side of a face: cell state +/- halved slope along the face normal, floors as :896-975
 // D: normal direction; sgn = +1 (upper face of the cell = left state of the face), -1 (lower face)
 // Sc: tile pointer of the cell (variable v at Sc[TL*v])
-template <int D>
+// PRHO: pressure floor smallp*rho (2-D trace, MHDBaseFunctor2D.h:985-1100) instead of smallp (3-D, :908)
+template <int D, bool PRHO = false>
 EK_HD MhdSide mhd_face_side(const Grid& g, const double* __restrict__ Sc, double sgn)
 {
   constexpr int SD = (D == 0) ? SX : (D == 1) ? SY : SZ;
@@ -292,7 +293,7 @@ EK_HD MhdSide mhd_face_side(const Grid& g, const double* __restrict__ Sc, double
   constexpr int KT2 = (D == 2) ? 5 : 6; // z: bt2 = A (slot 5);  x: bt2 = C (slot 6);  y: bt2 = C (slot 6)
   MhdSide s;
   s.r = dmax(g.smallr, Sc[TL * (SC + ID)] + sgn * Sc[TL * (SD + 0)]);
-  s.p = dmax(g.smallp, Sc[TL * (SC + IP)] + sgn * Sc[TL * (SD + 1)]);
+  s.p = dmax(PRHO ? g.smallp * s.r : g.smallp, Sc[TL * (SC + IP)] + sgn * Sc[TL * (SD + 1)]);
   s.un = Sc[TL * (SC + VN)] + sgn * Sc[TL * (SD + 2 + (VN - IU))];
   s.ut1 = Sc[TL * (SC + VT1)] + sgn * Sc[TL * (SD + 2 + (VT1 - IU))];
   s.ut2 = Sc[TL * (SC + VT2)] + sgn * Sc[TL * (SD + 2 + (VT2 - IU))];
@@ -325,7 +326,7 @@ EK_HD void mhd_face_flux(const Grid& g, const double* __restrict__ S, const MhdI
 }
 
 // one corner state of the edge along D3: cell tile pointer Sc, slopes applied with signs s1 (along D1), s2 (along D2)
-template <int D3>
+template <int D3, bool PRHO = false>
 EK_HD MhdCorner mhd_edge_corner(const Grid& g, const double* __restrict__ Sc, double s1, double s2, double a, double b)
 {
   constexpr int D1 = (D3 + 1) % 3, D2 = (D3 + 2) % 3;
@@ -337,7 +338,7 @@ EK_HD MhdCorner mhd_edge_corner(const Grid& g, const double* __restrict__ Sc, do
   constexpr int K2 = (D2 == 0) ? (D3 == 1 ? 5 : 6) : (D2 == 1) ? (D3 == 0 ? 5 : 6) : (D3 == 0 ? 5 : 6);
   MhdCorner c;
   c.r = dmax(g.smallr, Sc[TL * (SC + ID)] + (s1 * Sc[TL * (S1 + 0)] + s2 * Sc[TL * (S2 + 0)]));
-  c.p = dmax(g.smallp, Sc[TL * (SC + IP)] + (s1 * Sc[TL * (S1 + 1)] + s2 * Sc[TL * (S2 + 1)]));
+  c.p = dmax(PRHO ? g.smallp * c.r : g.smallp, Sc[TL * (SC + IP)] + (s1 * Sc[TL * (S1 + 1)] + s2 * Sc[TL * (S2 + 1)]));
   c.u = Sc[TL * (SC + IU + D1)] + (s1 * Sc[TL * (S1 + 2 + D1)] + s2 * Sc[TL * (S2 + 2 + D1)]);
   c.v = Sc[TL * (SC + IU + D2)] + (s1 * Sc[TL * (S1 + 2 + D2)] + s2 * Sc[TL * (S2 + 2 + D2)]);
   c.c = Sc[TL * (SC + IA + D3)] + (s1 * Sc[TL * (S1 + K1)] + s2 * Sc[TL * (S2 + K2)]);
@@ -348,7 +349,7 @@ EK_HD MhdCorner mhd_edge_corner(const Grid& g, const double* __restrict__ Sc, do
 
 // EMF at the lower edge of cell c that runs along D3 (compute_emf<EMFX|EMFY|EMFZ> with the corner
 // assignment of ComputeEmfAndStoreFunctor3D, MHDRunFunctors3D.h:2199-2226)
-template <int D3>
+template <int D3, bool PRHO = false>
 EK_HD double mhd_edge_emf(const Grid& g, const double* __restrict__ S, const MhdIdx& x)
 {
   constexpr int D1 = (D3 + 1) % 3, D2 = (D3 + 2) % 3;
@@ -366,10 +367,10 @@ EK_HD double mhd_edge_emf(const Grid& g, const double* __restrict__ S, const Mhd
   const double aHigh = S00[TL * F1] - S00[TL * DF1]; // aLR = aRR
   const double bLow = S10[TL * F2] + S10[TL * DF2];  // bLL = bLR
   const double bHigh = S00[TL * F2] - S00[TL * DF2]; // bRL = bRR
-  const MhdCorner LL = mhd_edge_corner<D3>(g, S11, +1.0, +1.0, aLow, bLow);
-  const MhdCorner RL = mhd_edge_corner<D3>(g, S01, -1.0, +1.0, aLow, bHigh);
-  const MhdCorner LR = mhd_edge_corner<D3>(g, S10, +1.0, -1.0, aHigh, bLow);
-  const MhdCorner RR = mhd_edge_corner<D3>(g, S00, -1.0, -1.0, aHigh, bHigh);
+  const MhdCorner LL = mhd_edge_corner<D3, PRHO>(g, S11, +1.0, +1.0, aLow, bLow);
+  const MhdCorner RL = mhd_edge_corner<D3, PRHO>(g, S01, -1.0, +1.0, aLow, bHigh);
+  const MhdCorner LR = mhd_edge_corner<D3, PRHO>(g, S10, +1.0, -1.0, aHigh, bLow);
+  const MhdCorner RR = mhd_edge_corner<D3, PRHO>(g, S00, -1.0, -1.0, aHigh, bHigh);
   return mhd_emf2d_hlld(g, LL, RL, LR, RR);
 }
 

@@ -2,7 +2,7 @@
 // mhd_cells.cuh.  One thread per cell of the ghosted box, flattened index (i fastest => coalesced,
 // no partially filled blocks along x for sizes like 518).
 #pragma once
-#include "mhd_cells.cuh"
+#include "mhd_cells2d.cuh"
 
 #ifndef EK_MHD_TRACE_PREFETCH
 #define EK_MHD_TRACE_PREFETCH 1
@@ -144,6 +144,90 @@ __global__ void __launch_bounds__(256) mhd_update_kernel(const MhdArgs a)
   MhdIdx x;
   if (mhd_cell_of_thread(a.g, x))
     mhd_stage_update(a.g, a.Uin, w.F, w.EMF, a.Uout, dt / a.g.dx, dt / a.g.dy, dt / a.g.dz, x);
+}
+
+// ---- MHD_Muscl_2D: same stages on the 2-D box (one thread per cell, flattened index) --------------
+__device__ __forceinline__ bool mhd2d_cell_of_thread(const Grid& g, MhdIdx& x)
+{
+  const unsigned c = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned sj = (unsigned)g.isize;
+  x.c = c;
+  x.sj = sj;
+  x.sk = 0;
+  x.k = 0;
+  if (c >= (unsigned)g.sv)
+    return false;
+  const unsigned j = c / sj;
+  x.j = (int)j;
+  x.i = (int)(c - j * sj);
+  return true;
+}
+
+__global__ void __launch_bounds__(256) mhd2d_prims_kernel(const MhdArgs a, const int do_invdt)
+{
+  if (a.ts->finished)
+    return;
+  const MhdWork2D w = mhd2d_work_split(a.work, a.g.sv);
+  MhdIdx x;
+  double m = 0.0;
+  if (mhd2d_cell_of_thread(a.g, x))
+    m = mhd2d_stage_prims(a.g, a.Uin, w.Q, x);
+  if (!do_invdt)
+    return;
+  __shared__ double red[8];
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0)
+    red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double r = (threadIdx.x < 8) ? red[threadIdx.x] : 0.0;
+    r = warp_max(r);
+    if (threadIdx.x == 0 && r > 0.0)
+      atomic_max_nonneg(&a.ts->invdt_bits, r);
+  }
+}
+
+__global__ void __launch_bounds__(256) mhd2d_elec_kernel(const MhdArgs a)
+{
+  if (a.ts->finished)
+    return;
+  const MhdWork2D w = mhd2d_work_split(a.work, a.g.sv);
+  MhdIdx x;
+  if (mhd2d_cell_of_thread(a.g, x))
+    mhd2d_stage_elec(a.g, a.Uin, w.Q, w.E, x);
+}
+
+__global__ void __launch_bounds__(256) mhd2d_trace_kernel(const MhdArgs a)
+{
+  if (a.ts->finished)
+    return;
+  const MhdWork2D w = mhd2d_work_split(a.work, a.g.sv);
+  const double dt = a.ts->dt;
+  MhdIdx x;
+  if (mhd2d_cell_of_thread(a.g, x))
+    mhd2d_stage_trace(a.g, a.Uin, w.Q, w.E, w.S, dt / a.g.dx, dt / a.g.dy, x);
+}
+
+template <int RS>
+__global__ void __launch_bounds__(128) mhd2d_faces_edge_kernel(const MhdArgs a)
+{
+  if (a.ts->finished)
+    return;
+  const MhdWork2D w = mhd2d_work_split(a.work, a.g.sv);
+  MhdIdx x;
+  if (mhd2d_cell_of_thread(a.g, x))
+    mhd2d_stage_faces_edge<RS>(a.g, w.S, w.F, w.EMF, x);
+}
+
+__global__ void __launch_bounds__(256) mhd2d_update_kernel(const MhdArgs a)
+{
+  if (a.ts->finished)
+    return;
+  const MhdWork2D w = mhd2d_work_split(a.work, a.g.sv);
+  const double dt = a.ts->dt;
+  MhdIdx x;
+  if (mhd2d_cell_of_thread(a.g, x))
+    mhd2d_stage_update(a.g, a.Uin, w.F, w.EMF, a.Uout, dt / a.g.dx, dt / a.g.dy, x);
 }
 
 } // namespace ek

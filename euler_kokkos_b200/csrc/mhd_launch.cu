@@ -7,7 +7,7 @@ namespace ek {
 
 size_t mhd_work_bytes(const Grid& g)
 {
-  return (size_t)W_TOTAL * (size_t)mhd_padded_cells(g.sv) * sizeof(double);
+  return (size_t)(g.ksize > 1 ? W_TOTAL : W2_TOTAL) * (size_t)mhd_padded_cells(g.sv) * sizeof(double);
 }
 
 static MhdArgs make_args(Ctx& c, const double* Uin, double* Uout)
@@ -26,10 +26,11 @@ static unsigned blocks(const Grid& g, int threads) { return (unsigned)((g.sv + t
 // primitives of the (ghost-filled) level + max inverse dt into ts->invdt_bits
 cudaError_t launch_mhd_invdt(Ctx& c, const double* U)
 {
-  if (c.p.dim != 3)
-    return cudaErrorNotSupported; // MHD_Muscl_2D: not implemented yet
   const MhdArgs a = make_args(c, U, nullptr);
-  mhd_prims_kernel<<<blocks(c.g, 256), 256, 0, c.stream>>>(a, 1);
+  if (c.p.dim == 2)
+    mhd2d_prims_kernel<<<blocks(c.g, 256), 256, 0, c.stream>>>(a, 1);
+  else
+    mhd_prims_kernel<<<blocks(c.g, 256), 256, 0, c.stream>>>(a, 1);
   c.launches++;
   c.mhd_prims_of = U;
   return cudaGetLastError();
@@ -59,10 +60,33 @@ static cudaError_t launch_step(Ctx& c, const double* Uin, double* Uout)
   return cudaGetLastError();
 }
 
+template <int RS>
+static cudaError_t launch_step_2d(Ctx& c, const double* Uin, double* Uout)
+{
+  const MhdArgs a = make_args(c, Uin, Uout);
+  if (c.mhd_prims_of != Uin) {
+    mhd2d_prims_kernel<<<blocks(c.g, 256), 256, 0, c.stream>>>(a, 0);
+    c.launches++;
+  }
+  c.mhd_prims_of = nullptr;
+  mhd2d_elec_kernel<<<blocks(c.g, 256), 256, 0, c.stream>>>(a);
+  mhd2d_trace_kernel<<<blocks(c.g, 256), 256, 0, c.stream>>>(a);
+  mhd2d_faces_edge_kernel<RS><<<blocks(c.g, 128), 128, 0, c.stream>>>(a);
+  mhd2d_update_kernel<<<blocks(c.g, 256), 256, 0, c.stream>>>(a);
+  c.launches += 4;
+  return cudaGetLastError();
+}
+
 cudaError_t launch_mhd_step(Ctx& c, const double* Uin, double* Uout)
 {
-  if (c.p.dim != 3)
-    return cudaErrorNotSupported;
+  if (c.p.dim == 2) {
+    switch (c.p.riemann) {
+      case RIEMANN_HLLD: return launch_step_2d<RIEMANN_HLLD>(c, Uin, Uout);
+      case RIEMANN_HLL: return launch_step_2d<RIEMANN_HLL>(c, Uin, Uout);
+      case RIEMANN_LLF: return launch_step_2d<RIEMANN_LLF>(c, Uin, Uout);
+      default: return cudaErrorInvalidValue;
+    }
+  }
   switch (c.p.riemann) {
     case RIEMANN_HLLD: return launch_step<RIEMANN_HLLD>(c, Uin, Uout);
     case RIEMANN_HLL: return launch_step<RIEMANN_HLL>(c, Uin, Uout);

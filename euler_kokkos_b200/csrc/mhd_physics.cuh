@@ -90,7 +90,9 @@ EK_HD double mhd_fast_speed2(double gamma0, double r, double p, double bn2, doub
 }
 
 // ---- HLLD (Miyoshi & Kusano 2005), hydro components of the flux only --------------------------
-// a = normal field (already the mean of both sides).  f = (mass, energy, normal, t1, t2 momentum).
+// a = normal field (already the mean of both sides).  f = (mass, energy, normal, t1, t2 momentum
+// [, flux of the second transverse field: only the 2-D solver advances Bz with it, MHDRunFunctors2D.h:1593-1625]).
+template <bool BT2>
 EK_HD void mhd_hlld(const Grid& g, const MhdSide& L, const MhdSide& R, double a, double* __restrict__ f)
 {
   const double entho = g.entho;
@@ -197,6 +199,8 @@ EK_HD void mhd_hlld(const Grid& g, const MhdSide& L, const MhdSide& R, double a,
   f[2] = fm * uo - a2 + ptoto;
   f[3] = fm * vo - a * bo;
   f[4] = fm * wo - a * co;
+  if constexpr (BT2)
+    f[5] = co * uo - a * wo;
 }
 
 // conservative variables and physical flux of one side (find_mhd_flux, mhd_utils.h:175-231), hydro comps
@@ -216,13 +220,16 @@ EK_HD void mhd_side_flux(double entho, const MhdSide& s, double a, double* __res
   ff[2] = s.r * s.un * s.un - a * a + ptot;
   ff[3] = s.r * s.un * s.ut1 - a * s.bt1;
   ff[4] = s.r * s.un * s.ut2 - a * s.bt2;
+  cv[5] = s.bt2;
+  ff[5] = s.bt2 * s.un - a * s.ut2;
 }
 
 // MHD HLL (RiemannSolvers_MHD.h:29-64)
+template <bool BT2>
 EK_HD void mhd_hll(const Grid& g, const MhdSide& L, const MhdSide& R, double a, double* __restrict__ f)
 {
   const double entho = g.entho;
-  double ul[5], fl[5], ur[5], fr[5];
+  double ul[6], fl[6], ur[6], fr[6];
   mhd_side_flux(entho, L, a, ul, fl);
   mhd_side_flux(entho, R, a, ur, fr);
   const double a2 = a * a;
@@ -232,15 +239,16 @@ EK_HD void mhd_hll(const Grid& g, const MhdSide& L, const MhdSide& R, double a, 
   const double sr = dmax(dmax(L.un, R.un) + cmax, 0.0);
   const double inv = rcp_fast(sr - sl);
 #pragma unroll
-  for (int v = 0; v < 5; ++v)
+  for (int v = 0; v < (BT2 ? 6 : 5); ++v)
     f[v] = (sr * fl[v] - sl * fr[v] + sr * sl * (ur[v] - ul[v])) * inv;
 }
 
 // MHD local Lax-Friedrichs (RiemannSolvers_MHD.h:80-108)
+template <bool BT2>
 EK_HD void mhd_llf(const Grid& g, const MhdSide& L, const MhdSide& R, double a, double* __restrict__ f)
 {
   const double entho = g.entho;
-  double ul[5], fl[5], ur[5], fr[5];
+  double ul[6], fl[6], ur[6], fr[6];
   mhd_side_flux(entho, L, a, ul, fl);
   mhd_side_flux(entho, R, a, ur, fr);
   const double a2 = a * a;
@@ -248,19 +256,19 @@ EK_HD void mhd_llf(const Grid& g, const MhdSide& L, const MhdSide& R, double a, 
   const double cr = sqrt_fast(mhd_fast_speed2(g.gamma0, R.r, R.p, a2, R.bt1 * R.bt1 + R.bt2 * R.bt2)) + fabs(R.un);
   const double vel = dmax(cl, cr);
 #pragma unroll
-  for (int v = 0; v < 5; ++v)
+  for (int v = 0; v < (BT2 ? 6 : 5); ++v)
     f[v] = (fl[v] + fr[v]) * 0.5 - vel * (ur[v] - ul[v]) * 0.5;
 }
 
-template <int RS>
+template <int RS, bool BT2 = false>
 EK_HD void mhd_riemann(const Grid& g, const MhdSide& L, const MhdSide& R, double a, double* __restrict__ f)
 {
   if constexpr (RS == RIEMANN_HLLD)
-    mhd_hlld(g, L, R, a, f);
+    mhd_hlld<BT2>(g, L, R, a, f);
   else if constexpr (RS == RIEMANN_HLL)
-    mhd_hll(g, L, R, a, f);
+    mhd_hll<BT2>(g, L, R, a, f);
   else
-    mhd_llf(g, L, R, a, f);
+    mhd_llf<BT2>(g, L, R, a, f);
 }
 
 // ---- 2-D HLLD magnetic Riemann solver at an edge ----------------------------------------------

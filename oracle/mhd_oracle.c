@@ -1,6 +1,6 @@
 /*
  * TEST INFRASTRUCTURE ONLY (see muscl_oracle.h) -- constrained-transport MHD part of the CPU
- * restatement: MHD_Muscl_3D, implementationVersion 0, staged exactly like the reference
+ * restatement: MHD_Muscl_3D and MHD_Muscl_2D, implementationVersion 0, staged exactly like the reference
  * (muscl/SolverMHDMuscl.cpp:463-513): ghost fill, copy, primitives, [dt], electric field,
  * magnetic slopes, trace (6 face + 12 edge states per cell), 3 HLLD fluxes per cell, 3 EMFs per
  * cell, flux update, CT update.  Same floating-point order as the reference functors, cell by cell.
@@ -76,6 +76,19 @@ static void constoprim_mhd(const orc_params* p, const double* u, const double* m
 void orc_mhd_prims(const orc_params* p, const double* U, double* Q)
 {
   const geom_t g = geom(p);
+  if (p->dim == 2) { /* muscl/MHDRunFunctors2D.h:85-160: magFieldNeighbors[IZ] = 0 */
+    for (int j = 0; j < g.jsize - 1; ++j)
+      for (int i = 0; i < g.isize - 1; ++i) {
+        double u[NV], q[NV], nb[3], c;
+        get_state(g, U, i, j, 0, u);
+        nb[0] = AT(U, i + 1, j, 0, IA);
+        nb[1] = AT(U, i, j + 1, 0, IB);
+        nb[2] = 0.0;
+        constoprim_mhd(p, u, nb, &c, q);
+        set_state(g, Q, i, j, 0, q);
+      }
+    return;
+  }
   for (int k = 0; k < g.ksize - 1; ++k)
     for (int j = 0; j < g.jsize - 1; ++j)
       for (int i = 0; i < g.isize - 1; ++i) {
@@ -95,6 +108,23 @@ double orc_mhd_invdt(const orc_params* p, const double* Q)
   const geom_t g = geom(p);
   const int gw = p->ghost;
   double invdt = 0.0;
+  if (p->dim == 2) { /* muscl/MHDRunFunctors2D.h:16-80, find_speed_info<TWO_D> */
+    for (int j = gw; j < g.jsize - gw; ++j)
+      for (int i = gw; i < g.isize - gw; ++i) {
+        double q[NV];
+        get_state(g, Q, i, j, 0, q);
+        const double d = q[ID], pp = q[IP], a = q[IA], b = q[IB], c = q[IC];
+        const double b2 = a * a + b * b + c * c;
+        const double c2 = p->gamma0 * pp / d;
+        const double d2 = 0.5 * (b2 / d + c2);
+        double cf = sqrt(d2 + sqrt(d2 * d2 - c2 * a * a / d));
+        const double vx = cf + fabs(q[IU]);
+        cf = sqrt(d2 + sqrt(d2 * d2 - c2 * b * b / d));
+        const double vy = cf + fabs(q[IV]);
+        invdt = fmax(invdt, vx / p->dx + vy / p->dy);
+      }
+    return invdt;
+  }
   for (int k = gw; k < g.ksize - gw; ++k)
     for (int j = gw; j < g.jsize - gw; ++j)
       for (int i = gw; i < g.isize - gw; ++i) {
@@ -662,11 +692,212 @@ static void trace_unsplit_mhd_3d_simpler(const orc_params* pr_, const double* q,
 }
 
 /* ------------------------------------------------------------------------------------------- */
+/* muscl/MHDBaseFunctor2D.h:776-1109 trace_unsplit_mhd_2d (Omega0 == 0); qNb[di][dj], bfNb[di][dj][3] */
+static void trace_unsplit_mhd_2d(const orc_params* pr_, double qNb[3][3][NV], double bfNb[4][4][3], double dtdx, double dtdy,
+                                 double qm[2][NV], double qp[2][NV], double qEdge[4][NV])
+{
+  enum { CENTER = 1 };
+  double* qRT = qEdge[0];
+  double* qRB = qEdge[1];
+  double* qLT = qEdge[2];
+  double* qLB = qEdge[3];
+  const double smallR = pr_->smallr, smallp = pr_->smallp, gamma = pr_->gamma0;
+  const double* q = qNb[CENTER][CENTER];
+  double Ez[2][2];
+  for (int di = 0; di < 2; di++)
+    for (int dj = 0; dj < 2; dj++) {
+      int cx = CENTER + di, cy = CENTER + dj;
+      double u = 0.25 * (qNb[cx - 1][cy - 1][IU] + qNb[cx - 1][cy][IU] + qNb[cx][cy - 1][IU] + qNb[cx][cy][IU]);
+      double v = 0.25 * (qNb[cx - 1][cy - 1][IV] + qNb[cx - 1][cy][IV] + qNb[cx][cy - 1][IV] + qNb[cx][cy][IV]);
+      double A = 0.5 * (bfNb[cx][cy - 1][0] + bfNb[cx][cy][0]);
+      double B = 0.5 * (bfNb[cx - 1][cy][1] + bfNb[cx][cy][1]);
+      Ez[di][dj] = u * B - v * A;
+    }
+  const double ELL = Ez[0][0], ELR = Ez[0][1], ERL = Ez[1][0], ERR = Ez[1][1];
+  double r = q[ID], p = q[IP], u = q[IU], v = q[IV], w = q[IW], A = q[IA], B = q[IB], C = q[IC];
+  double AL = bfNb[CENTER][CENTER][0], AR = bfNb[CENTER + 1][CENTER][0];
+  double BL = bfNb[CENTER][CENTER][1], BR = bfNb[CENTER][CENTER + 1][1];
+
+  /* slope_unsplit_hydro_2d (:347-390); slope_type other than 1, 2 leaves dq uninitialised in the reference: zero here */
+  double dq[2][NV];
+  const double st = pr_->slope_type;
+  for (int n = 0; n < NV; ++n) {
+    if (st == 1 || st == 2) {
+      dq[0][n] = slope1(st, q[n], qNb[CENTER + 1][CENTER][n], qNb[CENTER - 1][CENTER][n]);
+      dq[1][n] = slope1(st, q[n], qNb[CENTER][CENTER + 1][n], qNb[CENTER][CENTER - 1][n]);
+    } else {
+      dq[0][n] = dq[1][n] = 0.0;
+    }
+  }
+  double drx = dq[0][ID] * 0.5, dpx = dq[0][IP] * 0.5, dux = dq[0][IU] * 0.5, dvx = dq[0][IV] * 0.5, dwx = dq[0][IW] * 0.5;
+  double dCx = dq[0][IC] * 0.5, dBx = dq[0][IB] * 0.5;
+  double dry = dq[1][ID] * 0.5, dpy = dq[1][IP] * 0.5, duy = dq[1][IU] * 0.5, dvy = dq[1][IV] * 0.5, dwy = dq[1][IW] * 0.5;
+  double dCy = dq[1][IC] * 0.5, dAy = dq[1][IA] * 0.5;
+
+  /* slope_unsplit_mhd_2d (:456-509): slope_type used as is */
+  double dALy = 0.5 * slope1(st, bfNb[CENTER][CENTER][0], bfNb[CENTER][CENTER + 1][0], bfNb[CENTER][CENTER - 1][0]);
+  double dBLx = 0.5 * slope1(st, bfNb[CENTER][CENTER][1], bfNb[CENTER + 1][CENTER][1], bfNb[CENTER - 1][CENTER][1]);
+  double dARy = 0.5 * slope1(st, bfNb[CENTER + 1][CENTER][0], bfNb[CENTER + 1][CENTER + 1][0], bfNb[CENTER + 1][CENTER - 1][0]);
+  double dBRx = 0.5 * slope1(st, bfNb[CENTER][CENTER + 1][1], bfNb[CENTER + 1][CENTER + 1][1], bfNb[CENTER - 1][CENTER + 1][1]);
+
+  double dAx = 0.5 * (AR - AL);
+  double dBy = 0.5 * (BR - BL);
+  double sr0, su0, sv0, sw0, sp0, sA0, sB0, sC0, sAL0, sAR0, sBL0, sBR0;
+  sr0 = (-u * drx - dux * r) * dtdx + (-v * dry - dvy * r) * dtdy;
+  su0 = (-u * dux - dpx / r - B * dBx / r - C * dCx / r) * dtdx + (-v * duy + B * dAy / r) * dtdy;
+  sv0 = (-u * dvx + A * dBx / r) * dtdx + (-v * dvy - dpy / r - A * dAy / r - C * dCy / r) * dtdy;
+  sw0 = (-u * dwx + A * dCx / r) * dtdx + (-v * dwy + B * dCy / r) * dtdy;
+  sp0 = (-u * dpx - dux * gamma * p) * dtdx + (-v * dpy - dvy * gamma * p) * dtdy;
+  sA0 = (u * dBy + B * duy - v * dAy - A * dvy) * dtdy;
+  sB0 = (-u * dBx - B * dux + v * dAx + A * dvx) * dtdx;
+  sC0 = (w * dAx + A * dwx - u * dCx - C * dux) * dtdx + (-v * dCy - C * dvy + w * dBy + B * dwy) * dtdy;
+  sAL0 = +(ELR - ELL) * 0.5 * dtdy;
+  sAR0 = +(ERR - ERL) * 0.5 * dtdy;
+  sBL0 = -(ERL - ELL) * 0.5 * dtdx;
+  sBR0 = -(ERR - ELR) * 0.5 * dtdx;
+
+  r = r + sr0; u = u + su0; v = v + sv0; w = w + sw0; p = p + sp0; A = A + sA0; B = B + sB0; C = C + sC0;
+  AL = AL + sAL0; AR = AR + sAR0; BL = BL + sBL0; BR = BR + sBR0;
+
+#define FLOOR2(s)                       \
+  (s)[ID] = fmax(smallR, (s)[ID]);      \
+  (s)[IP] = fmax(smallp * (s)[ID], (s)[IP])
+  qp[0][ID] = r - drx; qp[0][IU] = u - dux; qp[0][IV] = v - dvx; qp[0][IW] = w - dwx; qp[0][IP] = p - dpx;
+  qp[0][IA] = AL; qp[0][IB] = B - dBx; qp[0][IC] = C - dCx; FLOOR2(qp[0]);
+  qm[0][ID] = r + drx; qm[0][IU] = u + dux; qm[0][IV] = v + dvx; qm[0][IW] = w + dwx; qm[0][IP] = p + dpx;
+  qm[0][IA] = AR; qm[0][IB] = B + dBx; qm[0][IC] = C + dCx; FLOOR2(qm[0]);
+  qp[1][ID] = r - dry; qp[1][IU] = u - duy; qp[1][IV] = v - dvy; qp[1][IW] = w - dwy; qp[1][IP] = p - dpy;
+  qp[1][IA] = A - dAy; qp[1][IB] = BL; qp[1][IC] = C - dCy; FLOOR2(qp[1]);
+  qm[1][ID] = r + dry; qm[1][IU] = u + duy; qm[1][IV] = v + dvy; qm[1][IW] = w + dwy; qm[1][IP] = p + dpy;
+  qm[1][IA] = A + dAy; qm[1][IB] = BR; qm[1][IC] = C + dCy; FLOOR2(qm[1]);
+
+  qRT[ID] = r + (+drx + dry); qRT[IU] = u + (+dux + duy); qRT[IV] = v + (+dvx + dvy); qRT[IW] = w + (+dwx + dwy);
+  qRT[IP] = p + (+dpx + dpy); qRT[IA] = AR + (+dARy); qRT[IB] = BR + (+dBRx); qRT[IC] = C + (+dCx + dCy); FLOOR2(qRT);
+  qRB[ID] = r + (+drx - dry); qRB[IU] = u + (+dux - duy); qRB[IV] = v + (+dvx - dvy); qRB[IW] = w + (+dwx - dwy);
+  qRB[IP] = p + (+dpx - dpy); qRB[IA] = AR + (-dARy); qRB[IB] = BL + (+dBLx); qRB[IC] = C + (+dCx - dCy); FLOOR2(qRB);
+  qLB[ID] = r + (-drx - dry); qLB[IU] = u + (-dux - duy); qLB[IV] = v + (-dvx - dvy); qLB[IW] = w + (-dwx - dwy);
+  qLB[IP] = p + (-dpx - dpy); qLB[IA] = AL + (-dALy); qLB[IB] = BL + (-dBLx); qLB[IC] = C + (-dCx - dCy); FLOOR2(qLB);
+  qLT[ID] = r + (-drx + dry); qLT[IU] = u + (-dux + duy); qLT[IV] = v + (-dvx + dvy); qLT[IW] = w + (-dwx + dwy);
+  qLT[IP] = p + (-dpx + dpy); qLT[IA] = AL + (+dALy); qLT[IB] = BR + (-dBRx); qLT[IC] = C + (-dCx + dCy); FLOOR2(qLT);
+#undef FLOOR2
+}
+
+/* muscl/SolverMHDMuscl.cpp:371-454 godunov_unsplit_impl<2>, implementationVersion 0 */
+static void mhd_step_2d(const orc_params* p, double* Uin, double* Uout, double dt, double t, double t_end, double* dt_used)
+{
+  const geom_t g = geom(p);
+  const int gw = p->ghost;
+  const int isize = g.isize, jsize = g.jsize;
+  const size_t ncell = g.sv, nstate = g.sv * NV;
+
+  orc_make_boundaries(p, Uin);
+  memcpy(Uout, Uin, nstate * sizeof(double));
+  double* Q = calloc(nstate, sizeof(double));
+  orc_mhd_prims(p, Uin, Q);
+  if (dt < 0) {
+    dt = p->cfl / orc_mhd_invdt(p, Q);
+    if (t + dt > t_end)
+      dt = t_end - t;
+  }
+  if (dt_used)
+    *dt_used = dt;
+  const double dtdx = dt / p->dx, dtdy = dt / p->dy;
+
+  /* ComputeTraceFunctor2D_MHD, muscl/MHDRunFunctors2D.h:782-905 */
+  double* Qm[2];
+  double* Qp[2];
+  double* QE[4];
+  for (int d = 0; d < 2; ++d) {
+    Qm[d] = calloc(nstate, sizeof(double));
+    Qp[d] = calloc(nstate, sizeof(double));
+  }
+  for (int e = 0; e < 4; ++e)
+    QE[e] = calloc(nstate, sizeof(double));
+  for (int j = gw - 2; j < jsize - gw + 1; ++j)
+    for (int i = gw - 2; i < isize - gw + 1; ++i) {
+      double qNb[3][3][NV], bfNb[4][4][3], qm[2][NV], qp[2][NV], qEdge[4][NV];
+      for (int di = 0; di < 3; di++)
+        for (int dj = 0; dj < 3; dj++)
+          get_state(g, Q, i + di - 1, j + dj - 1, 0, qNb[di][dj]);
+      for (int di = 0; di < 4; di++)
+        for (int dj = 0; dj < 4; dj++) {
+          bfNb[di][dj][0] = AT(Uin, i + di - 1, j + dj - 1, 0, IA);
+          bfNb[di][dj][1] = AT(Uin, i + di - 1, j + dj - 1, 0, IB);
+          bfNb[di][dj][2] = AT(Uin, i + di - 1, j + dj - 1, 0, IC);
+        }
+      trace_unsplit_mhd_2d(p, qNb, bfNb, dtdx, dtdy, qm, qp, qEdge);
+      for (int d = 0; d < 2; ++d) {
+        set_state(g, Qm[d], i, j, 0, qm[d]);
+        set_state(g, Qp[d], i, j, 0, qp[d]);
+      }
+      for (int e = 0; e < 4; ++e)
+        set_state(g, QE[e], i, j, 0, qEdge[e]);
+    }
+
+  /* ComputeFluxesAndStoreFunctor2D_MHD (:375-470) + ComputeEmfAndStoreFunctor2D (:612-686) */
+  double* F[2];
+  for (int d = 0; d < 2; ++d)
+    F[d] = calloc(nstate, sizeof(double));
+  double* Emf = calloc(ncell, sizeof(double));
+  for (int j = gw; j < jsize - gw + 1; ++j)
+    for (int i = gw; i < isize - gw + 1; ++i) {
+      double ql[NV], qr[NV], flux[NV];
+      memset(flux, 0, sizeof flux);
+      get_state(g, Qm[0], i - 1, j, 0, ql);
+      get_state(g, Qp[0], i, j, 0, qr);
+      riemann_mhd(p, ql, qr, flux);
+      set_state(g, F[0], i, j, 0, flux);
+      get_state(g, Qm[1], i, j - 1, 0, ql);
+      swapv(&ql[IU], &ql[IV]);
+      swapv(&ql[IA], &ql[IB]);
+      get_state(g, Qp[1], i, j, 0, qr);
+      swapv(&qr[IU], &qr[IV]);
+      swapv(&qr[IA], &qr[IB]);
+      riemann_mhd(p, ql, qr, flux);
+      set_state(g, F[1], i, j, 0, flux);
+
+      double qe[4][NV];
+      get_state(g, QE[IRT], i - 1, j - 1, 0, qe[IRT]);
+      get_state(g, QE[IRB], i - 1, j, 0, qe[IRB]);
+      get_state(g, QE[ILT], i, j - 1, 0, qe[ILT]);
+      get_state(g, QE[ILB], i, j, 0, qe[ILB]);
+      AT(Emf, i, j, 0, 0) = compute_emf(p, EMFZ, qe);
+    }
+
+  /* UpdateFunctor2D_MHD (:1539-1640) then UpdateEmfFunctor2D (:1646-1700) */
+  for (int j = gw; j < jsize - gw; ++j)
+    for (int i = gw; i < isize - gw; ++i) {
+      double u[NV], f[NV];
+      get_state(g, Uout, i, j, 0, u);
+      get_state(g, F[0], i, j, 0, f);
+      u[ID] += f[ID] * dtdx; u[IP] += f[IP] * dtdx; u[IU] += f[IU] * dtdx; u[IV] += f[IV] * dtdx; u[IW] += f[IW] * dtdx; u[IC] += f[IC] * dtdx;
+      get_state(g, F[0], i + 1, j, 0, f);
+      u[ID] -= f[ID] * dtdx; u[IP] -= f[IP] * dtdx; u[IU] -= f[IU] * dtdx; u[IV] -= f[IV] * dtdx; u[IW] -= f[IW] * dtdx; u[IC] -= f[IC] * dtdx;
+      get_state(g, F[1], i, j, 0, f);
+      u[ID] += f[ID] * dtdy; u[IP] += f[IP] * dtdy; u[IU] += f[IV] * dtdy; u[IV] += f[IU] * dtdy; u[IW] += f[IW] * dtdy; u[IC] += f[IC] * dtdy;
+      get_state(g, F[1], i, j + 1, 0, f);
+      u[ID] -= f[ID] * dtdy; u[IP] -= f[IP] * dtdy; u[IU] -= f[IV] * dtdy; u[IV] -= f[IU] * dtdy; u[IW] -= f[IW] * dtdy; u[IC] -= f[IC] * dtdy;
+      u[IA] += (AT(Emf, i, j + 1, 0, 0) - AT(Emf, i, j, 0, 0)) * dtdy;
+      u[IB] -= (AT(Emf, i + 1, j, 0, 0) - AT(Emf, i, j, 0, 0)) * dtdx;
+      set_state(g, Uout, i, j, 0, u);
+    }
+
+  free(Q); free(Emf);
+  for (int d = 0; d < 2; ++d) {
+    free(Qm[d]); free(Qp[d]); free(F[d]);
+  }
+  for (int e = 0; e < 4; ++e)
+    free(QE[e]);
+}
+
+/* ------------------------------------------------------------------------------------------- */
 /* muscl/SolverMHDMuscl.cpp:463-513 godunov_unsplit_impl<3>, implementationVersion 0 */
 void orc_mhd_step(const orc_params* p, double* Uin, double* Uout, double dt, double t, double t_end, double* dt_used)
 {
-  if (p->dim != 3)
-    abort(); /* MHD_Muscl_2D is not restated yet */
+  if (p->dim == 2) {
+    mhd_step_2d(p, Uin, Uout, dt, t, t_end, dt_used);
+    return;
+  }
   const geom_t g = geom(p);
   const int gw = p->ghost;
   const int isize = g.isize, jsize = g.jsize, ksize = g.ksize;

@@ -7,7 +7,7 @@
 #include <vector>
 
 #include "../../euler_kokkos_b200/csrc/ek_grid.h"
-#include "../../euler_kokkos_b200/csrc/mhd_cells.cuh"
+#include "../../euler_kokkos_b200/csrc/mhd_cells2d.cuh"
 
 using namespace ek;
 
@@ -34,14 +34,30 @@ static void step(const Grid& g, const double* Uin, double* Uout, double* work, d
   LOOP mhd_stage_update(g, Uin, w.F, w.EMF, Uout, dtdx, dtdy, dtdz, x);
 }
 
+template <int RS>
+static void step2d(const Grid& g, const double* Uin, double* Uout, double* work, double dt)
+{
+  const MhdWork2D w = mhd2d_work_split(work, g.sv);
+  const double dtdx = dt / g.dx, dtdy = dt / g.dy;
+  LOOP mhd2d_stage_elec(g, Uin, w.Q, w.E, x);
+  LOOP mhd2d_stage_trace(g, Uin, w.Q, w.E, w.S, dtdx, dtdy, x);
+  LOOP mhd2d_stage_faces_edge<RS>(g, w.S, w.F, w.EMF, x);
+  LOOP mhd2d_stage_update(g, Uin, w.F, w.EMF, Uout, dtdx, dtdy, x);
+}
+
 extern "C" {
 
 // max inverse dt of a ghost-filled state (stage P); Q is left in `work`
 double emul_mhd_invdt(const ek_params* p, const double* U, double* work)
 {
   const Grid g = make_grid(*p);
-  const MhdWork w = mhd_work_split(work, g.sv);
   double m = 0.0;
+  if (g.ksize == 1) {
+    const MhdWork2D w2 = mhd2d_work_split(work, g.sv);
+    LOOP m = fmax(m, mhd2d_stage_prims(g, U, w2.Q, x));
+    return m;
+  }
+  const MhdWork w = mhd_work_split(work, g.sv);
   LOOP m = fmax(m, mhd_stage_prims(g, U, w.Q, x));
   return m;
 }
@@ -53,6 +69,14 @@ int emul_mhd_step(const ek_params* p, const double* Uin, double* Uout, double* w
 {
   const Grid g = make_grid(*p);
   emul_mhd_invdt(p, Uin, work);
+  if (p->dim == 2) {
+    switch (p->riemann) {
+      case RIEMANN_HLLD: step2d<RIEMANN_HLLD>(g, Uin, Uout, work, dt); return 0;
+      case RIEMANN_HLL: step2d<RIEMANN_HLL>(g, Uin, Uout, work, dt); return 0;
+      case RIEMANN_LLF: step2d<RIEMANN_LLF>(g, Uin, Uout, work, dt); return 0;
+    }
+    return 1;
+  }
   switch (p->riemann) {
     case RIEMANN_HLLD: step<RIEMANN_HLLD>(g, Uin, Uout, work, dt); return 0;
     case RIEMANN_HLL: step<RIEMANN_HLL>(g, Uin, Uout, work, dt); return 0;

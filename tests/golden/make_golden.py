@@ -50,6 +50,13 @@ CASES = {
                             "mesh.boundary_type_ymax": 1, "mesh.boundary_type_zmin": 1, "mesh.boundary_type_zmax": 1}, 8, (1, 4, 8)),
     "blast3d_hllc_big": ("test_blast_3D.ini", {"mesh.nx": 20, "mesh.ny": 16, "mesh.nz": 12, "blast.radius": 0.35,
                                                "mesh.boundary_type_xmin": 2, "mesh.boundary_type_ymax": 3, "mesh.boundary_type_ymin": 3}, 8, (1, 8)),
+    "ot2d_hlld": ("test_mhd_orszag_tang_2D.ini", {"mesh.nx": 48, "mesh.ny": 40}, 10, (1, 2, 10)),
+    "ot2d_hlld_slope1": ("test_mhd_orszag_tang_2D.ini", {"mesh.nx": 32, "mesh.ny": 32, "hydro.slope_type": 1}, 4, (1, 4)),
+    "ot2d_hll": ("test_mhd_orszag_tang_2D.ini", {"mesh.nx": 32, "mesh.ny": 24, "hydro.riemann": "hll"}, 3, (1, 3)),
+    "mhdblast2d_hlld_bc": ("/root/reference/settings/test_mhd_blast_2D.ini",
+                           {"mesh.nx": 32, "mesh.ny": 28, "blast.radius": 0.3, "other.implementationversion": 0, "run.solver_name": "MHD_Muscl_2D",
+                            "mesh.boundary_type_xmin": 1, "mesh.boundary_type_xmax": 2, "mesh.boundary_type_ymin": 3,
+                            "mesh.boundary_type_ymax": 3}, 10, (1, 5, 10)),
     "ot3d_llf": ("test_mhd_orszag_tang_3D.ini", {"mesh.nx": 16, "mesh.ny": 12, "mesh.nz": 8, "hydro.riemann": "llf"}, 3, (1, 3)),
 }
 

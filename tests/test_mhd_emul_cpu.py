@@ -30,7 +30,8 @@ def _one_step_chain(p, U, nsteps):
     return worst
 
 
-@pytest.mark.parametrize("name", ["ot3d_hlld", "ot3d_hlld_slope1", "ot3d_hll", "ot3d_llf", "mhdblast3d_hlld", "mhdblast3d_hlld_bc"])
+@pytest.mark.parametrize("name", ["ot3d_hlld", "ot3d_hlld_slope1", "ot3d_hll", "ot3d_llf", "mhdblast3d_hlld", "mhdblast3d_hlld_bc",
+                                  "ot2d_hlld", "ot2d_hlld_slope1", "ot2d_hll", "mhdblast2d_hlld_bc"])
 def test_emul_on_reference_states(name):
     """one-step parity starting from states dumped by the reference binary (incl. shocked MHD blast)."""
     from euler_kokkos_b200.vti import embed_interior
@@ -49,4 +50,13 @@ def test_emul_random_states(riemann, bc):
     p = util.make_params(dim=3, mhd=True, n=(13, 11, 9), riemann=riemann, bc=bc, smallr=1e-8, smallc=1e-8,
                          box=((0, 1.0), (0, 0.8), (0, 0.5)))
     U = util.random_hydro_state(p, seed=11, mach=2.5)
+    _one_step_chain(p, U, 3)
+
+
+@pytest.mark.parametrize("riemann", ["hlld", "hll", "llf"])
+@pytest.mark.parametrize("bc", [(3, 3, 3, 3, 0, 0), (1, 2, 2, 1, 0, 0)])
+def test_emul_random_states_2d(riemann, bc):
+    p = util.make_params(dim=2, mhd=True, n=(23, 17, 1), riemann=riemann, bc=bc, smallr=1e-7, smallc=1e-7,
+                         box=((0, 1.0), (0, 0.8), (0, 1.0)))
+    U = util.random_hydro_state(p, seed=12, mach=2.5)
     _one_step_chain(p, U, 3)

@@ -33,7 +33,8 @@ def _check_steps(p, U0, nsteps, tol=TOL):
     return worst
 
 
-@pytest.mark.parametrize("name", ["ot3d_hlld", "ot3d_hlld_slope1", "ot3d_hll", "ot3d_llf", "mhdblast3d_hlld", "mhdblast3d_hlld_bc"])
+@pytest.mark.parametrize("name", ["ot3d_hlld", "ot3d_hlld_slope1", "ot3d_hll", "ot3d_llf", "mhdblast3d_hlld", "mhdblast3d_hlld_bc",
+                                  "ot2d_hlld", "ot2d_hlld_slope1", "ot2d_hll", "mhdblast2d_hlld_bc"])
 def test_mhd3d_one_step_on_reference_states(name):
     """one-step parity from states dumped by the reference binary (tests/golden)."""
     from euler_kokkos_b200.vti import embed_interior
@@ -54,13 +55,21 @@ def test_mhd3d_random_states(riemann, n, bc):
     _check_steps(p, util.random_hydro_state(p, seed=21, mach=2.5), 3)
 
 
+@pytest.mark.parametrize("riemann", ["hlld", "hll", "llf"])
+@pytest.mark.parametrize("n,bc", [((23, 17, 1), (3, 3, 3, 3, 0, 0)), ((130, 67, 1), (1, 2, 2, 1, 0, 0))])
+def test_mhd2d_random_states(riemann, n, bc):
+    p = util.make_params(dim=2, mhd=True, n=n, riemann=riemann, bc=bc, smallr=1e-7, smallc=1e-7,
+                         box=((0, 1.0), (0, 0.8), (0, 1.0)))
+    _check_steps(p, util.random_hydro_state(p, seed=22, mach=2.5), 3)
+
+
 def test_mhd3d_golden_free_run_device_dt():
     """ek_run (device-resident dt, MHD dt computed after the ghost fill) vs the reference's own dumps."""
     from euler_kokkos_b200 import capi
     from euler_kokkos_b200.vti import embed_interior
     from tests.test_oracle_golden import load_case
 
-    for name in ("ot3d_hlld", "mhdblast3d_hlld_bc"):
+    for name in ("ot3d_hlld", "mhdblast3d_hlld_bc", "ot2d_hlld", "mhdblast2d_hlld_bc"):
         z, case = load_case(name)
         p = case.params
         ctx = capi.Context(p)
