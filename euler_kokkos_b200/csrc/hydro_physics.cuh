@@ -397,12 +397,15 @@ __device__ __forceinline__ void riemann_hllc_n(const Grid& g, const double (*ql)
     const double rstar = ro_[n] * (S[n] - uo_[n]) * is[n];
     const double estar = ((S[n] - uo_[n]) * eo_[n] - po_[n] * uo_[n] + pstar[n] * ustar[n]) * is[n];
     // the state sampled at x/t = 0: upwind state if the fan does not contain 0, else the star state
-    const bool sup_l = SL[n] > 0.0;
-    const bool sup_r = !sup_l && !(ustar[n] > 0.0) && !(SR[n] > 0.0);
-    const double ro = sup_l ? rl[n] : sup_r ? rr[n] : rstar;
-    const double uo = sup_l ? ql[n][IU] : sup_r ? qr[n][IU] : ustar[n];
-    const double po = sup_l ? pl[n] : sup_r ? pr[n] : pstar[n];
-    const double eo = sup_l ? etotl[n] : sup_r ? etotr[n] : estar;
+    // Sampling at x/t = 0.  The reference tests SL > 0, ustar > 0, SR > 0 in turn (RiemannSolvers.h:528-553).
+    // Because rcl*(ul-SL) >= gamma*pl and rcr*(ur-SL) >= gamma*pr, SL > 0 implies ustar > 0 (and SR <= 0 implies
+    // ustar <= 0), so the side picked by the sign of ustar already is the upwind side of the supersonic cases:
+    // star state iff SL <= 0 < SR, otherwise the state of that side.
+    const bool star = !(SL[n] > 0.0) && (SR[n] > 0.0);
+    const double ro = star ? rstar : ro_[n];
+    const double uo = star ? ustar[n] : uo_[n];
+    const double po = star ? pstar[n] : po_[n];
+    const double eo = star ? estar : eo_[n];
     const double fm = ro * uo;
     flux[n][ID] = fm;
     flux[n][IU] = fm * uo + po;
