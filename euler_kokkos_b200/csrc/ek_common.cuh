@@ -37,6 +37,7 @@ struct Grid {
   double invdx, invdy, invdz; // 1/dx, 1/dy, 1/dz (IEEE, computed on the host)
   double gamma0, gamma6, smallr, smallc, smallp, smallpp, cfl, slope_type;
   double entho;               // 1/(gamma0-1)
+  double slope_k;             // 0.5/slope_type (limited_slope_ref)
   int bc[6];
   int impl_version;
   int gravity_hancock;
@@ -54,18 +55,20 @@ EK_HD double dmin(double a, double b) { return (a < b) ? a : b; }
 // evaluated with 8 FP64-pipe operations: "dlft*drgt <= 0" is decided on the sign bits (a zero factor
 // makes the min zero anyway) and sign(dcen) is transplanted with copysign (when the signs of dlft and
 // drgt agree, dcen has that sign too; the sign of a zero result is immaterial).
-EK_HD double limited_slope_ref(double st, double qm, double q, double qp)
+// sk = 0.5/st.  For st in {1, 2} (the only non-zero values the reference supports) the scalings by st
+// and sk are exact, so st*min(|a|,|b|,sk*|c|) == min(|st*a|,|st*b|,|c/2|) bit for bit: 7 FP64 operations.
+EK_HD double limited_slope_ref(double st, double sk, double qm, double q, double qp)
 {
-  const double dl = st * (q - qm);
-  const double dr = st * (qp - q);
-  const double dc = 0.5 * (qp - qm);
-  const double m = dmin(dmin(fabs(dl), fabs(dr)), fabs(dc));
+  const double a = q - qm;
+  const double b = qp - q;
+  const double c = qp - qm;
+  const double m = st * dmin(dmin(fabs(a), fabs(b)), sk * fabs(c));
 #ifdef __CUDA_ARCH__
-  const bool opposite = (__double2hiint(dl) ^ __double2hiint(dr)) < 0;
+  const bool opposite = (__double2hiint(a) ^ __double2hiint(b)) < 0;
 #else
-  const bool opposite = std::signbit(dl) != std::signbit(dr);
+  const bool opposite = std::signbit(a) != std::signbit(b);
 #endif
-  return opposite ? 0.0 : copysign(m, dc);
+  return opposite ? 0.0 : copysign(m, c);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -122,6 +125,24 @@ EK_HD double sqrt_fast(double x)
   const double d = fma(-g, g, x);
   g = fma(d, h, g);
   return (x >= 2.2250738585072014e-308) ? g : 0.0;
+#endif
+}
+
+// sqrt for finite normal x > 0 (no zero guard)
+EK_HD double sqrt_pos_fast(double x)
+{
+#if EK_PRECISE_MATH || !defined(__CUDA_ARCH__)
+  return sqrt(x);
+#else
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double g = x * y;
+  double h = 0.5 * y;
+  const double r = fma(-h, g, 0.5);
+  g = fma(g, r, g);
+  h = fma(h, r, h);
+  const double d = fma(-g, g, x);
+  return fma(d, h, g);
 #endif
 }
 

@@ -21,6 +21,7 @@ inline Grid make_grid(const ek_params& p)
   g.dx = p.dx; g.dy = p.dy; g.dz = p.dz;
   g.invdx = 1.0 / p.dx; g.invdy = 1.0 / p.dy; g.invdz = (p.dim == 3) ? 1.0 / p.dz : 0.0;
   g.entho = 1.0 / (p.gamma0 - 1.0);
+  g.slope_k = (p.slope_type > 0.0) ? 0.5 / p.slope_type : 0.0;
   g.gamma0 = p.gamma0; g.gamma6 = p.gamma6; g.smallr = p.smallr; g.smallc = p.smallc;
   g.smallp = p.smallp; g.smallpp = p.smallpp; g.cfl = p.cfl; g.slope_type = p.slope_type;
   for (int f = 0; f < 6; ++f) g.bc[f] = p.bc[f];

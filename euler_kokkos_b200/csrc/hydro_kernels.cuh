@@ -142,10 +142,10 @@ __global__ void __launch_bounds__(32 * (TY + 4), 1) hydro_step_kernel(const Hydr
       for (int v = 0; v < NV; ++v) {
         const double c = q0[v * PLANE + so];
         qc[v] = c;
-        dq[0][v] = limited_slope(st, q0[v * PLANE + so - 1], c, q0[v * PLANE + so + 1]);
-        dq[1][v] = limited_slope(st, q0[v * PLANE + so - 32], c, q0[v * PLANE + so + 32]);
+        dq[0][v] = limited_slope(st, g.slope_k, q0[v * PLANE + so - 1], c, q0[v * PLANE + so + 1]);
+        dq[1][v] = limited_slope(st, g.slope_k, q0[v * PLANE + so - 32], c, q0[v * PLANE + so + 32]);
         if constexpr (DIM == 3)
-          dq[2][v] = limited_slope(st, sm.q[sm1][v * PLANE + so], c, sm.q[sp1][v * PLANE + so]);
+          dq[2][v] = limited_slope(st, g.slope_k, sm.q[sm1][v * PLANE + so], c, sm.q[sp1][v * PLANE + so]);
       }
       if (st == 0.0) { // slope_type 0: first-order (HydroBaseFunctor3D.h:498-520)
 #pragma unroll
@@ -164,15 +164,21 @@ __global__ void __launch_bounds__(32 * (TY + 4), 1) hydro_step_kernel(const Hydr
             gh[c] = 0.5 * dt * __ldg(a.grav + col + g.sk * p + g.sv * c);
         }
       }
+      // face states q -/+ dq/2 + s*dt/(2 dx) [+ gravity predictor]: the cell-centred half-step value is formed
+      // once per direction (one FMA), the two faces are one FMA each
+      const double dth[3] = { dtd[0] * 0.5, dtd[1] * 0.5, dtd[2] * 0.5 };
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
-        const double add = (v >= IU) ? gh[v - IU] : 0.0;
-        const double sx = s[v] * (dtd[0] * 0.5), sy = s[v] * (dtd[1] * 0.5);
-        const double hx = 0.5 * dq[0][v], hy = 0.5 * dq[1][v];
-        lo[0][v] = (qc[v] - hx) + sx + add;
-        lo[1][v] = (qc[v] - hy) + sy + add;
-        double mxv = (qc[v] + hx) + sx + add;
-        double myv = (qc[v] + hy) + sy + add;
+        const double add = (GRAV && v >= IU) ? gh[v - IU] : 0.0;
+        double bx = fma(s[v], dth[0], qc[v]), by = fma(s[v], dth[1], qc[v]);
+        if constexpr (GRAV) {
+          bx += add;
+          by += add;
+        }
+        lo[0][v] = fma(-0.5, dq[0][v], bx);
+        lo[1][v] = fma(-0.5, dq[1][v], by);
+        double mxv = fma(0.5, dq[0][v], bx);
+        double myv = fma(0.5, dq[1][v], by);
         if (v == ID) {
           lo[0][v] = dmax(g.smallr, lo[0][v]);
           lo[1][v] = dmax(g.smallr, lo[1][v]);
@@ -182,13 +188,16 @@ __global__ void __launch_bounds__(32 * (TY + 4), 1) hydro_step_kernel(const Hydr
         sm.mx[v * PLANE + so] = mxv;
         sm.my[v * PLANE + so] = myv;
         if constexpr (DIM == 3) {
-          const double sz = s[v] * (dtd[2] * 0.5);
-          const double hz = 0.5 * dq[2][v];
-          // implementationVersion 1 omits the gravity predictor on the ZMIN-face state
-          // (HydroRunFunctors3D.h:1351 vs :1277-1285)
-          const double addz = (g.impl_version == 1) ? 0.0 : add;
-          lo[2][v] = (qc[v] - hz) + sz + addz;
-          double mzv = (qc[v] + hz) + sz + add;
+          const double bz0 = fma(s[v], dth[2], qc[v]);
+          double bzl = bz0, bzh = bz0;
+          if constexpr (GRAV) {
+            // implementationVersion 1 omits the gravity predictor on the ZMIN-face state
+            // (HydroRunFunctors3D.h:1351 vs :1277-1285)
+            bzl += (g.impl_version == 1) ? 0.0 : add;
+            bzh += add;
+          }
+          lo[2][v] = fma(-0.5, dq[2][v], bzl);
+          double mzv = fma(0.5, dq[2][v], bzh);
           if (v == ID) {
             lo[2][v] = dmax(g.smallr, lo[2][v]);
             mzv = dmax(g.smallr, mzv);

@@ -73,9 +73,9 @@ __device__ __forceinline__ double hydro_cell_invdt(const Grid& g, const double* 
 }
 
 // ---- limited slope ---------------------------------------------------------------------------
-__device__ __forceinline__ double limited_slope(double st, double qm, double q, double qp)
+__device__ __forceinline__ double limited_slope(double st, double sk, double qm, double q, double qp)
 {
-  return limited_slope_ref(st, qm, q, qp);
+  return limited_slope_ref(st, sk, qm, q, qp);
 }
 
 // ---- Hancock predictor: source terms of one cell ---------------------------------------------
@@ -335,9 +335,11 @@ __device__ __forceinline__ void riemann_hllc_n(const Grid& g, const double (*ql)
   double rl[N], pl[N], rr[N], pr[N], etotl[N], etotr[N], cmax[N], SL[N], SR[N], ustar[N], pstar[N];
 #pragma unroll
   for (int n = 0; n < N; ++n) {
-    rl[n] = dmax(ql[n][ID], g.smallr);
+    // the traced states already carry the density floor (trace_unsplit_*: rho = max(smallr, .)), so the
+    // reference's max(rho, smallr) here is the identity
+    rl[n] = ql[n][ID];
     pl[n] = dmax(ql[n][IP], rl[n] * g.smallp);
-    rr[n] = dmax(qr[n][ID], g.smallr);
+    rr[n] = qr[n][ID];
     pr[n] = dmax(qr[n][IP], rr[n] * g.smallp);
   }
 #pragma unroll
@@ -361,7 +363,7 @@ __device__ __forceinline__ void riemann_hllc_n(const Grid& g, const double (*ql)
   }
 #pragma unroll
   for (int n = 0; n < N; ++n)
-    cmax[n] = sqrt_fast(dmax(dmax(c2l[n], c2r[n]), sc2));
+    cmax[n] = sqrt_pos_fast(dmax(dmax(c2l[n], c2r[n]), sc2)); // argument >= smallc^2 > 0
   double irc[N], rcl[N], rcr[N];
 #pragma unroll
   for (int n = 0; n < N; ++n) {

@@ -173,20 +173,20 @@ EK_HD void mhd_stage_trace(const Grid& g, const double* __restrict__ U, const do
   if (in_j && in_k) {
     const double GLR = Ej[2 * TL], FLR = Ek[TL];
     Sc[TL * SFA] = AL + (+(GLR - GLL) * dtdy * 0.5 - (FLR - FLL) * dtdz * 0.5);
-    Sc[TL * SDAY] = 0.5 * mhd_slope(xst, UA[-sj], AL, UA[sj]);
-    Sc[TL * SDAZ] = 0.5 * mhd_slope(xst, UA[-sk], AL, UA[sk]);
+    Sc[TL * SDAY] = mhd_half_slope(0.5 * xst, g.slope_k, UA[-sj], AL, UA[sj]);
+    Sc[TL * SDAZ] = mhd_half_slope(0.5 * xst, g.slope_k, UA[-sk], AL, UA[sk]);
   }
   if (in_i && in_k) {
     const double GRL = Ei[2 * TL], ELR = Ek[0];
     Sc[TL * SFB] = BL + (-(GRL - GLL) * dtdx * 0.5 + (ELR - ELL) * dtdz * 0.5);
-    Sc[TL * SDBX] = 0.5 * mhd_slope(xst, UB[-1], BL, UB[1]);
-    Sc[TL * SDBZ] = 0.5 * mhd_slope(xst, UB[-sk], BL, UB[sk]);
+    Sc[TL * SDBX] = mhd_half_slope(0.5 * xst, g.slope_k, UB[-1], BL, UB[1]);
+    Sc[TL * SDBZ] = mhd_half_slope(0.5 * xst, g.slope_k, UB[-sk], BL, UB[sk]);
   }
   if (in_i && in_j) {
     const double FRL = Ei[TL], ERL = Ej[0];
     Sc[TL * SFC] = CL + (+(FRL - FLL) * dtdx * 0.5 - (ERL - ELL) * dtdy * 0.5);
-    Sc[TL * SDCX] = 0.5 * mhd_slope(xst, UC[-1], CL, UC[1]);
-    Sc[TL * SDCY] = 0.5 * mhd_slope(xst, UC[-sj], CL, UC[sj]);
+    Sc[TL * SDCX] = mhd_half_slope(0.5 * xst, g.slope_k, UC[-1], CL, UC[1]);
+    Sc[TL * SDCY] = mhd_half_slope(0.5 * xst, g.slope_k, UC[-sj], CL, UC[sj]);
   }
   if (!(in_i && in_j && in_k))
     return;
@@ -194,6 +194,7 @@ EK_HD void mhd_stage_trace(const Grid& g, const double* __restrict__ U, const do
   // cell-centred half step, accumulated direction by direction (x, then y, then z: the reference's
   // own summation order) so that only one direction's slopes are live at a time
   const double st = g.slope_type;
+  const double sth = 0.5 * st;
   const bool use_slopes = (st == 1.0 || st == 2.0); // slope_unsplit_hydro_3d, :379,:470
   const double* __restrict__ Q0 = Q + tile_off<8>(c);
   double q[8];
@@ -210,7 +211,7 @@ EK_HD void mhd_stage_trace(const Grid& g, const double* __restrict__ U, const do
     double d[8];
 #pragma unroll
     for (int n = 0; n < 8; ++n)
-      d[n] = (use_slopes && n != IA) ? 0.5 * mhd_slope(st, Qm[TL * n], q[n], Qp[TL * n]) : 0.0;
+      d[n] = (use_slopes && n != IA) ? mhd_half_slope(sth, g.slope_k, Qm[TL * n], q[n], Qp[TL * n]) : 0.0;
     const double drx = d[ID], dpx = d[IP], dux = d[IU], dvx = d[IV], dwx = d[IW], dBx = d[IB], dCx = d[IC];
     const double dAx = 0.5 * (UA[1] - AL);
     sr0 = (-u * drx - dux * r) * dtdx;
@@ -229,7 +230,7 @@ EK_HD void mhd_stage_trace(const Grid& g, const double* __restrict__ U, const do
     double d[8];
 #pragma unroll
     for (int n = 0; n < 8; ++n)
-      d[n] = (use_slopes && n != IB) ? 0.5 * mhd_slope(st, Qm[TL * n], q[n], Qp[TL * n]) : 0.0;
+      d[n] = (use_slopes && n != IB) ? mhd_half_slope(sth, g.slope_k, Qm[TL * n], q[n], Qp[TL * n]) : 0.0;
     const double dry = d[ID], dpy = d[IP], duy = d[IU], dvy = d[IV], dwy = d[IW], dAy = d[IA], dCy = d[IC];
     const double dBy = 0.5 * (UB[sj] - BL);
     sr0 += (-v * dry - dvy * r) * dtdy;
@@ -248,7 +249,7 @@ EK_HD void mhd_stage_trace(const Grid& g, const double* __restrict__ U, const do
     double d[8];
 #pragma unroll
     for (int n = 0; n < 8; ++n)
-      d[n] = (use_slopes && n != IC) ? 0.5 * mhd_slope(st, Qm[TL * n], q[n], Qp[TL * n]) : 0.0;
+      d[n] = (use_slopes && n != IC) ? mhd_half_slope(sth, g.slope_k, Qm[TL * n], q[n], Qp[TL * n]) : 0.0;
     const double drz = d[ID], dpz = d[IP], duz = d[IU], dvz = d[IV], dwz = d[IW], dAz = d[IA], dBz = d[IB];
     const double dCz = 0.5 * (UC[sk] - CL);
     sr0 += (-w * drz - dwz * r) * dtdz;

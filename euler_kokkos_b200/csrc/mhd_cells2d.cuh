@@ -106,18 +106,19 @@ EK_HD void mhd2d_stage_trace(const Grid& g, const double* __restrict__ U, const 
   const double* __restrict__ UB = U + sv * IB + c;
   const bool in_i = x.i <= g.isize - 3, in_j = x.j <= g.jsize - 3;
   const double st = g.slope_type;
+  const double sth = 0.5 * st;
   double* __restrict__ Sc = S + tile_off<S_TOTAL>(c);
   const double AL = UA[0], BL = UB[0];
   const double ELL = E[tile_off<1>(c)];
   if (in_j) {
     const double ELR = E[tile_off<1>(c + x.sj)];
     Sc[TL * SFA] = AL + (+(ELR - ELL) * 0.5 * dtdy);
-    Sc[TL * SDAY] = 0.5 * mhd_slope(st, UA[-sj], AL, UA[sj]);
+    Sc[TL * SDAY] = mhd_half_slope(sth, g.slope_k, UA[-sj], AL, UA[sj]);
   }
   if (in_i) {
     const double ERL = E[tile_off<1>(c + 1)];
     Sc[TL * SFB] = BL + (-(ERL - ELL) * 0.5 * dtdx);
-    Sc[TL * SDBX] = 0.5 * mhd_slope(st, UB[-1], BL, UB[1]);
+    Sc[TL * SDBX] = mhd_half_slope(sth, g.slope_k, UB[-1], BL, UB[1]);
   }
   if (!(in_i && in_j))
     return;
@@ -138,7 +139,7 @@ EK_HD void mhd2d_stage_trace(const Grid& g, const double* __restrict__ U, const 
     double d[8];
 #pragma unroll
     for (int n = 0; n < 8; ++n)
-      d[n] = (use_slopes && n != IA) ? 0.5 * mhd_slope(st, Qm[TL * n], q[n], Qp[TL * n]) : 0.0;
+      d[n] = (use_slopes && n != IA) ? mhd_half_slope(sth, g.slope_k, Qm[TL * n], q[n], Qp[TL * n]) : 0.0;
     const double drx = d[ID], dpx = d[IP], dux = d[IU], dvx = d[IV], dwx = d[IW], dBx = d[IB], dCx = d[IC];
     const double dAx = 0.5 * (UA[1] - AL);
     sr0 = (-u * drx - dux * r) * dtdx;
@@ -157,7 +158,7 @@ EK_HD void mhd2d_stage_trace(const Grid& g, const double* __restrict__ U, const 
     double d[8];
 #pragma unroll
     for (int n = 0; n < 8; ++n)
-      d[n] = (use_slopes && n != IB) ? 0.5 * mhd_slope(st, Qm[TL * n], q[n], Qp[TL * n]) : 0.0;
+      d[n] = (use_slopes && n != IB) ? mhd_half_slope(sth, g.slope_k, Qm[TL * n], q[n], Qp[TL * n]) : 0.0;
     const double dry = d[ID], dpy = d[IP], duy = d[IU], dvy = d[IV], dwy = d[IW], dAy = d[IA], dCy = d[IC];
     const double dBy = 0.5 * (UB[sj] - BL);
     sr0 += (-v * dry - dvy * r) * dtdy;

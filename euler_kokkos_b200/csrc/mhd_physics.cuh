@@ -38,9 +38,10 @@ struct MhdCorner {
 
 // limited slope (slope_unsplit_hydro_3d_scalar, MHDBaseFunctor3D.h:320-337; the same formula is used
 // for the face-centred field in slope_unsplit_mhd_3d, :563-668)
-EK_HD double mhd_slope(double st, double qm, double q, double qp)
+// HALF of the limited slope (what the trace uses): sth = slope_type/2, sk = 0.5/slope_type
+EK_HD double mhd_half_slope(double sth, double sk, double qm, double q, double qp)
 {
-  return limited_slope_ref(st, qm, q, qp);
+  return limited_slope_ref(sth, sk, qm, q, qp);
 }
 
 // ---- conservative -> primitive (cell-centred B = mean of the two faces) -----------------------
