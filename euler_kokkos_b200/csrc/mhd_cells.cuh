@@ -82,6 +82,87 @@ struct MhdIdx {
   int i, j, k;
 };
 
+// Thread -> cell map of the stencil stages ("y-chunked"): the ghosted box is cut into slabs of `yc`
+// rows; inside a slab the order is k (slowest), then j, then i.  Two consecutive planes of a slab are
+// then only yc*isize cells apart in launch order instead of a full plane, so the k-1 / k+1 neighbour
+// lines a stage reads are still in L2 when they are needed again (at 518^2 cells x 38 doubles a full
+// plane of S is 82 MB; ncu showed S being read 1.7x and Q 2.7x with the flat order).  Each slab-plane
+// is a contiguous range of the flat cell index; it is widened to 32-cell boundaries so that warps stay
+// aligned with the AoSoA tiles (lanes that fall into the neighbouring slab are masked).
+//   t: linear thread index;  returns false for masked threads.   yc <= 0: flat order (t == c).
+struct MhdChunkMap {
+  unsigned yc;     // rows per slab
+  unsigned nchunk; // slabs
+  unsigned span;   // threads per slab-plane: yc*isize rounded up to tiles + 1 tile
+  unsigned kg;     // consecutive planes handled by consecutive warps (one CTA = kg warps = the same 32-cell
+                   // segment in kg planes: the k-1 / k+1 lines of one warp are the own lines of its CTA mates => L1 hits)
+  unsigned kpad;   // ksize rounded up to a multiple of kg
+};
+EK_HD MhdChunkMap mhd_chunk_map(const Grid& g, int yc, int kg = 1)
+{
+  MhdChunkMap m;
+  m.yc = (yc <= 0) ? 0u : (unsigned)(yc < g.jsize ? yc : g.jsize);
+  m.kg = (kg < 1) ? 1u : (unsigned)kg;
+  m.kpad = (((unsigned)g.ksize + m.kg - 1) / m.kg) * m.kg;
+  if (m.yc == 0) {
+    m.nchunk = 1;
+    m.span = 0;
+    return m;
+  }
+  m.nchunk = ((unsigned)g.jsize + m.yc - 1) / m.yc;
+  m.span = ((m.yc * (unsigned)g.isize + 31u) & ~31u) + 32u;
+  return m;
+}
+EK_HD unsigned long long mhd_chunk_threads(const Grid& g, const MhdChunkMap& m)
+{
+  if (m.yc == 0)
+    return (unsigned long long)g.sv;
+  return (unsigned long long)m.nchunk * m.kpad * m.span;
+}
+EK_HD bool mhd_chunk_cell(const Grid& g, const MhdChunkMap& m, unsigned t, MhdIdx& x)
+{
+  const unsigned sj = (unsigned)g.isize, sk = (unsigned)g.sk;
+  x.sj = sj;
+  x.sk = sk;
+  unsigned c;
+  if (m.yc == 0) {
+    c = t;
+    if (c >= (unsigned)g.sv)
+      return false;
+  } else {
+    const unsigned per_chunk = m.span * m.kpad;
+    const unsigned ch = t / per_chunk;
+    if (ch >= m.nchunk)
+      return false;
+    const unsigned r = t - ch * per_chunk;
+    // inside a slab: groups of kg planes; inside a group: 32-cell segment (slowest), plane, lane
+    const unsigned per_group = m.span * m.kg;
+    const unsigned kgi = r / per_group;
+    const unsigned rr = r - kgi * per_group;
+    const unsigned seg = rr / (32u * m.kg);
+    const unsigned rw = rr - seg * (32u * m.kg);
+    const unsigned k = kgi * m.kg + (rw >> 5);
+    if (k >= (unsigned)g.ksize)
+      return false;
+    const unsigned o = seg * 32u + (rw & 31u);
+    const unsigned j0 = ch * m.yc;
+    const unsigned j1 = (j0 + m.yc < (unsigned)g.jsize) ? j0 + m.yc : (unsigned)g.jsize;
+    const unsigned c0 = sj * j0 + sk * k;       // first cell of the slab-plane
+    const unsigned c1 = sj * j1 + sk * k;       // one past its last cell
+    c = (c0 & ~31u) + o;
+    if (c < c0 || c >= c1)
+      return false;
+  }
+  x.c = c;
+  const unsigned k = c / sk;
+  const unsigned r = c - k * sk;
+  const unsigned j = r / sj;
+  x.k = (int)k;
+  x.j = (int)j;
+  x.i = (int)(r - j * sj);
+  return true;
+}
+
 // ---- stage P ------------------------------------------------------------------------------------
 // Q(i,j,k) for 0 <= i < isize-1 (the last layer is never written, MHDRunFunctors3D.h:120-122);
 // returns the cell's inverse-dt contribution (0 outside the interior).

@@ -16,7 +16,13 @@ struct MhdArgs {
   double* __restrict__ Uout;
   double* __restrict__ work;
   TimeState* ts;
+  MhdChunkMap cm; // thread -> cell order of the 3-D stencil stages (yc = 0: flat)
 };
+
+__device__ __forceinline__ bool mhd_cell_of_thread(const MhdArgs& a, MhdIdx& x)
+{
+  return mhd_chunk_cell(a.g, a.cm, blockIdx.x * blockDim.x + threadIdx.x, x);
+}
 
 __device__ __forceinline__ bool mhd_cell_of_thread(const Grid& g, MhdIdx& x)
 {
@@ -67,7 +73,7 @@ __global__ void __launch_bounds__(256) mhd_elec_kernel(const MhdArgs a)
     return;
   const MhdWork w = mhd_work_split(a.work, a.g.sv);
   MhdIdx x;
-  if (mhd_cell_of_thread(a.g, x))
+  if (mhd_cell_of_thread(a, x))
     mhd_stage_elec(a.g, a.Uin, w.Q, w.E, x);
 }
 
@@ -81,7 +87,7 @@ __global__ void __launch_bounds__(256, EK_MHD_TRACE_MINB) mhd_trace_kernel(const
   const MhdWork w = mhd_work_split(a.work, a.g.sv);
   const double dt = a.ts->dt;
   MhdIdx x;
-  if (mhd_cell_of_thread(a.g, x)) {
+  if (mhd_cell_of_thread(a, x)) {
 #if EK_MHD_TRACE_PREFETCH
     // the stage walks x, then y, then z: pull the y/z neighbour lines of Q towards L2 while the x
     // part waits on DRAM (the kernel is latency bound: ~80 independent loads per cell, 80 registers)
@@ -106,7 +112,7 @@ __global__ void __launch_bounds__(128) mhd_flux_kernel(const MhdArgs a)
     return;
   const MhdWork w = mhd_work_split(a.work, a.g.sv);
   MhdIdx x;
-  if (mhd_cell_of_thread(a.g, x))
+  if (mhd_cell_of_thread(a, x))
     mhd_stage_fluxes<RS>(a.g, w.S, w.F, x);
 }
 
@@ -116,20 +122,23 @@ __global__ void __launch_bounds__(128) mhd_emf_kernel(const MhdArgs a)
     return;
   const MhdWork w = mhd_work_split(a.work, a.g.sv);
   MhdIdx x;
-  if (mhd_cell_of_thread(a.g, x))
+  if (mhd_cell_of_thread(a, x))
     mhd_stage_emfs(a.g, w.S, w.EMF, x);
 }
 
 // stage R in one pass: the three face fluxes, then the three edge EMFs of the same cell (the S
 // lines of the cell and its neighbours are read once from HBM and served from L1/L2 the second time)
+#ifndef EK_MHD_R_MINB
+#define EK_MHD_R_MINB 4
+#endif
 template <int RS>
-__global__ void __launch_bounds__(128, 4) mhd_faces_edges_kernel(const MhdArgs a)
+__global__ void __launch_bounds__(128, EK_MHD_R_MINB) mhd_faces_edges_kernel(const MhdArgs a)
 {
   if (a.ts->finished)
     return;
   const MhdWork w = mhd_work_split(a.work, a.g.sv);
   MhdIdx x;
-  if (mhd_cell_of_thread(a.g, x)) {
+  if (mhd_cell_of_thread(a, x)) {
     mhd_stage_fluxes<RS>(a.g, w.S, w.F, x);
     mhd_stage_emfs(a.g, w.S, w.EMF, x);
   }
@@ -142,7 +151,7 @@ __global__ void __launch_bounds__(256) mhd_update_kernel(const MhdArgs a)
   const MhdWork w = mhd_work_split(a.work, a.g.sv);
   const double dt = a.ts->dt;
   MhdIdx x;
-  if (mhd_cell_of_thread(a.g, x))
+  if (mhd_cell_of_thread(a, x))
     mhd_stage_update(a.g, a.Uin, w.F, w.EMF, a.Uout, dt / a.g.dx, dt / a.g.dy, dt / a.g.dz, x);
 }
 

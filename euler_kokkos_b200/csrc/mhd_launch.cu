@@ -18,10 +18,26 @@ static MhdArgs make_args(Ctx& c, const double* Uin, double* Uout)
   a.Uout = Uout;
   a.work = c.work;
   a.ts = c.ts;
+  // rows per slab of the y-chunked launch order (mhd_cells.cuh); EK_MHD_YCHUNK=0 restores the flat order
+  const int ychunk = getenv("EK_MHD_YCHUNK") ? atoi(getenv("EK_MHD_YCHUNK")) : 16;
+  a.cm = mhd_chunk_map(c.g, c.g.ksize > 1 ? ychunk : 0, 1);
+  return a;
+}
+
+// the same arguments with consecutive warps of a CTA of `threads` threads mapped to consecutive planes
+static MhdArgs zgrouped(const Ctx& c, MhdArgs a, int threads)
+{
+  const int zg = getenv("EK_MHD_ZGROUP") ? atoi(getenv("EK_MHD_ZGROUP")) : 0; // 0: one plane per CTA (measured: no gain from L1 sharing between planes)
+  if (zg && a.cm.yc)
+    a.cm = mhd_chunk_map(c.g, (int)a.cm.yc, threads / 32);
   return a;
 }
 
 static unsigned blocks(const Grid& g, int threads) { return (unsigned)((g.sv + threads - 1) / threads); }
+static unsigned blocks(const MhdArgs& a, int threads)
+{
+  return (unsigned)((mhd_chunk_threads(a.g, a.cm) + (unsigned)threads - 1) / (unsigned)threads);
+}
 
 // primitives of the (ghost-filled) level + max inverse dt into ts->invdt_bits
 cudaError_t launch_mhd_invdt(Ctx& c, const double* U)
@@ -45,18 +61,19 @@ static cudaError_t launch_step(Ctx& c, const double* Uin, double* Uout)
     c.launches++;
   }
   c.mhd_prims_of = nullptr;
-  mhd_elec_kernel<<<blocks(c.g, 256), 256, 0, c.stream>>>(a);
-  mhd_trace_kernel<<<blocks(c.g, 256), 256, 0, c.stream>>>(a);
-  static const int fuse_r = getenv("EK_MHD_FUSE_R") ? atoi(getenv("EK_MHD_FUSE_R")) : 1; // tuning switch (default: fused)
+  const MhdArgs a8 = zgrouped(c, a, 256), a4 = zgrouped(c, a, 128);
+  mhd_elec_kernel<<<blocks(a8, 256), 256, 0, c.stream>>>(a8);
+  mhd_trace_kernel<<<blocks(a8, 256), 256, 0, c.stream>>>(a8);
+  const int fuse_r = getenv("EK_MHD_FUSE_R") ? atoi(getenv("EK_MHD_FUSE_R")) : 1; // tuning switch (default: fused)
   if (fuse_r) {
-    mhd_faces_edges_kernel<RS><<<blocks(c.g, 128), 128, 0, c.stream>>>(a);
+    mhd_faces_edges_kernel<RS><<<blocks(a4, 128), 128, 0, c.stream>>>(a4);
     c.launches += 4;
   } else {
-    mhd_flux_kernel<RS><<<blocks(c.g, 128), 128, 0, c.stream>>>(a);
-    mhd_emf_kernel<<<blocks(c.g, 128), 128, 0, c.stream>>>(a);
+    mhd_flux_kernel<RS><<<blocks(a4, 128), 128, 0, c.stream>>>(a4);
+    mhd_emf_kernel<<<blocks(a4, 128), 128, 0, c.stream>>>(a4);
     c.launches += 5;
   }
-  mhd_update_kernel<<<blocks(c.g, 256), 256, 0, c.stream>>>(a);
+  mhd_update_kernel<<<blocks(a8, 256), 256, 0, c.stream>>>(a8);
   return cudaGetLastError();
 }
 

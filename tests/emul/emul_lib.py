@@ -20,6 +20,8 @@ def lib():
         _lib.emul_mhd_work_len.restype = C.c_longlong
         _lib.emul_mhd_work_len.argtypes = [C.c_void_p]
         _lib.emul_mhd_step.argtypes = [C.c_void_p, dp, dp, dp, C.c_double]
+        _lib.emul_chunk_map_check.restype = C.c_longlong
+        _lib.emul_chunk_map_check.argtypes = [C.c_int] * 5
     return _lib
 
 
@@ -39,3 +41,7 @@ def mhd_step(p, U, dt):
     rc = lib().emul_mhd_step(C.byref(p), _dp(U), _dp(out), _dp(work), float(dt))
     assert rc == 0
     return out
+
+
+def chunk_map_violations(isize, jsize, ksize, yc, kg=1):
+    return lib().emul_chunk_map_check(isize, jsize, ksize, yc, kg)

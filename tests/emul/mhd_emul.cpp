@@ -84,4 +84,29 @@ int emul_mhd_step(const ek_params* p, const double* Uin, double* Uout, double* w
   }
   return 1;
 }
+
+// the y-chunked launch order of the 3-D stencil kernels (mhd_chunk_cell): every cell of the ghosted box
+// must be produced by exactly one thread, with thread%32 == cell%32 (warps aligned to the AoSoA tiles).
+// Returns the number of violations.
+long long emul_chunk_map_check(int isize, int jsize, int ksize, int yc, int kg)
+{
+  Grid g{};
+  g.isize = isize; g.jsize = jsize; g.ksize = ksize;
+  g.sj = isize; g.sk = (long long)isize * jsize; g.sv = g.sk * ksize;
+  const MhdChunkMap m = mhd_chunk_map(g, yc, kg);
+  const unsigned long long nt = mhd_chunk_threads(g, m);
+  std::vector<unsigned char> seen((size_t)g.sv, 0);
+  long long bad = 0;
+  for (unsigned long long t = 0; t < nt + 64; ++t) {
+    MhdIdx x;
+    if (!mhd_chunk_cell(g, m, (unsigned)t, x))
+      continue;
+    if (x.c >= (unsigned)g.sv || (x.c & 31u) != ((unsigned)t & 31u) ||
+        (unsigned)x.i + (unsigned)isize * ((unsigned)x.j + (unsigned)jsize * (unsigned)x.k) != x.c || seen[x.c]++)
+      ++bad;
+  }
+  for (size_t c = 0; c < seen.size(); ++c)
+    bad += (seen[c] != 1);
+  return bad;
+}
 }

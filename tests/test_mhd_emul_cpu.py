@@ -60,3 +60,14 @@ def test_emul_random_states_2d(riemann, bc):
                          box=((0, 1.0), (0, 0.8), (0, 1.0)))
     U = util.random_hydro_state(p, seed=12, mach=2.5)
     _one_step_chain(p, U, 3)
+
+
+@pytest.mark.parametrize("shape,yc", [((70, 70, 22), 32), ((38, 37, 14), 8), ((134, 29, 9), 5), ((22, 18, 30), 0), ((22, 18, 30), 18),
+                                      ((518, 70, 6), 32), ((33, 65, 7), 64)])
+@pytest.mark.parametrize("kg", [1, 4, 8])
+def test_chunked_launch_order_covers_every_cell_once(shape, yc, kg):
+    """mhd_chunk_cell (the thread -> cell map of the 3-D stencil kernels): a bijection onto the ghosted box that
+    keeps warps aligned with the AoSoA tiles."""
+    from tests.emul import emul_lib as E
+
+    assert E.chunk_map_violations(*shape, yc, kg) == 0
