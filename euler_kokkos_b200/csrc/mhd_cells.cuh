@@ -358,8 +358,15 @@ EK_HD void mhd_stage_trace(const Grid& g, const double* __restrict__ U, const do
 // D: normal direction; sgn = +1 (upper face of the cell = left state of the face), -1 (lower face)
 // Sc: tile pointer of the cell (variable v at Sc[TL*v])
 // PRHO: pressure floor smallp*rho (2-D trace, MHDBaseFunctor2D.h:985-1100) instead of smallp (3-D, :908)
-template <int D, bool PRHO = false>
-EK_HD MhdSide mhd_face_side(const Grid& g, const double* __restrict__ Sc, double sgn)
+// The value source is a "view" v with v(var) = variable var of the compact state S of one cell: a tile pointer
+// (TileRef, below) or the per-lane staging columns of the software-pipelined kernel (mhd_staged.cuh).
+struct TileRef {
+  const double* __restrict__ p;
+  EK_HD double operator()(int var) const { return p[TL * var]; }
+};
+
+template <int D, bool PRHO = false, class V>
+EK_HD MhdSide mhd_face_side_v(const Grid& g, const V& Sc, double sgn)
 {
   constexpr int SD = (D == 0) ? SX : (D == 1) ? SY : SZ;
   // velocity / field components in the face-normal frame (the reference swaps IU<->IV, IA<->IB for y
@@ -374,14 +381,20 @@ EK_HD MhdSide mhd_face_side(const Grid& g, const double* __restrict__ Sc, double
   constexpr int KT1 = (D == 2) ? 6 : 5; // z: bt1 = B (slot 6);  x: bt1 = B (slot 5);  y: bt1 = A (slot 5)
   constexpr int KT2 = (D == 2) ? 5 : 6; // z: bt2 = A (slot 5);  x: bt2 = C (slot 6);  y: bt2 = C (slot 6)
   MhdSide s;
-  s.r = dmax(g.smallr, Sc[TL * (SC + ID)] + sgn * Sc[TL * (SD + 0)]);
-  s.p = dmax(PRHO ? g.smallp * s.r : g.smallp, Sc[TL * (SC + IP)] + sgn * Sc[TL * (SD + 1)]);
-  s.un = Sc[TL * (SC + VN)] + sgn * Sc[TL * (SD + 2 + (VN - IU))];
-  s.ut1 = Sc[TL * (SC + VT1)] + sgn * Sc[TL * (SD + 2 + (VT1 - IU))];
-  s.ut2 = Sc[TL * (SC + VT2)] + sgn * Sc[TL * (SD + 2 + (VT2 - IU))];
-  s.bt1 = Sc[TL * (SC + BT1)] + sgn * Sc[TL * (SD + KT1)];
-  s.bt2 = Sc[TL * (SC + BT2)] + sgn * Sc[TL * (SD + KT2)];
+  s.r = dmax(g.smallr, Sc(SC + ID) + sgn * Sc(SD + 0));
+  s.p = dmax(PRHO ? g.smallp * s.r : g.smallp, Sc(SC + IP) + sgn * Sc(SD + 1));
+  s.un = Sc(SC + VN) + sgn * Sc(SD + 2 + (VN - IU));
+  s.ut1 = Sc(SC + VT1) + sgn * Sc(SD + 2 + (VT1 - IU));
+  s.ut2 = Sc(SC + VT2) + sgn * Sc(SD + 2 + (VT2 - IU));
+  s.bt1 = Sc(SC + BT1) + sgn * Sc(SD + KT1);
+  s.bt2 = Sc(SC + BT2) + sgn * Sc(SD + KT2);
   return s;
+}
+
+template <int D, bool PRHO = false>
+EK_HD MhdSide mhd_face_side(const Grid& g, const double* __restrict__ Sc, double sgn)
+{
+  return mhd_face_side_v<D, PRHO>(g, TileRef{ Sc }, sgn);
 }
 
 // flux through the lower D-face of cell c: f = (mass, energy, mom_x, mom_y, mom_z)
@@ -408,8 +421,8 @@ EK_HD void mhd_face_flux(const Grid& g, const double* __restrict__ S, const MhdI
 }
 
 // one corner state of the edge along D3: cell tile pointer Sc, slopes applied with signs s1 (along D1), s2 (along D2)
-template <int D3, bool PRHO = false>
-EK_HD MhdCorner mhd_edge_corner(const Grid& g, const double* __restrict__ Sc, double s1, double s2, double a, double b)
+template <int D3, bool PRHO = false, class V>
+EK_HD MhdCorner mhd_edge_corner_v(const Grid& g, const V& Sc, double s1, double s2, double a, double b)
 {
   constexpr int D1 = (D3 + 1) % 3, D2 = (D3 + 2) % 3;
   constexpr int S1 = (D1 == 0) ? SX : (D1 == 1) ? SY : SZ;
@@ -419,14 +432,20 @@ EK_HD MhdCorner mhd_edge_corner(const Grid& g, const double* __restrict__ Sc, do
   constexpr int K1 = (D1 == 0) ? (D3 == 1 ? 5 : 6) : (D1 == 1) ? (D3 == 0 ? 5 : 6) : (D3 == 0 ? 5 : 6);
   constexpr int K2 = (D2 == 0) ? (D3 == 1 ? 5 : 6) : (D2 == 1) ? (D3 == 0 ? 5 : 6) : (D3 == 0 ? 5 : 6);
   MhdCorner c;
-  c.r = dmax(g.smallr, Sc[TL * (SC + ID)] + (s1 * Sc[TL * (S1 + 0)] + s2 * Sc[TL * (S2 + 0)]));
-  c.p = dmax(PRHO ? g.smallp * c.r : g.smallp, Sc[TL * (SC + IP)] + (s1 * Sc[TL * (S1 + 1)] + s2 * Sc[TL * (S2 + 1)]));
-  c.u = Sc[TL * (SC + IU + D1)] + (s1 * Sc[TL * (S1 + 2 + D1)] + s2 * Sc[TL * (S2 + 2 + D1)]);
-  c.v = Sc[TL * (SC + IU + D2)] + (s1 * Sc[TL * (S1 + 2 + D2)] + s2 * Sc[TL * (S2 + 2 + D2)]);
-  c.c = Sc[TL * (SC + IA + D3)] + (s1 * Sc[TL * (S1 + K1)] + s2 * Sc[TL * (S2 + K2)]);
+  c.r = dmax(g.smallr, Sc(SC + ID) + (s1 * Sc(S1 + 0) + s2 * Sc(S2 + 0)));
+  c.p = dmax(PRHO ? g.smallp * c.r : g.smallp, Sc(SC + IP) + (s1 * Sc(S1 + 1) + s2 * Sc(S2 + 1)));
+  c.u = Sc(SC + IU + D1) + (s1 * Sc(S1 + 2 + D1) + s2 * Sc(S2 + 2 + D1));
+  c.v = Sc(SC + IU + D2) + (s1 * Sc(S1 + 2 + D2) + s2 * Sc(S2 + 2 + D2));
+  c.c = Sc(SC + IA + D3) + (s1 * Sc(S1 + K1) + s2 * Sc(S2 + K2));
   c.a = a;
   c.b = b;
   return c;
+}
+
+template <int D3, bool PRHO = false>
+EK_HD MhdCorner mhd_edge_corner(const Grid& g, const double* __restrict__ Sc, double s1, double s2, double a, double b)
+{
+  return mhd_edge_corner_v<D3, PRHO>(g, TileRef{ Sc }, s1, s2, a, b);
 }
 
 // EMF at the lower edge of cell c that runs along D3 (compute_emf<EMFX|EMFY|EMFZ> with the corner

@@ -240,3 +240,5 @@ __global__ void __launch_bounds__(256) mhd2d_update_kernel(const MhdArgs a)
 }
 
 } // namespace ek
+
+#include "mhd_staged.cuh"

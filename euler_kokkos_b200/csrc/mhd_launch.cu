@@ -65,7 +65,23 @@ static cudaError_t launch_step(Ctx& c, const double* Uin, double* Uout)
   mhd_elec_kernel<<<blocks(a8, 256), 256, 0, c.stream>>>(a8);
   mhd_trace_kernel<<<blocks(a8, 256), 256, 0, c.stream>>>(a8);
   const int fuse_r = getenv("EK_MHD_FUSE_R") ? atoi(getenv("EK_MHD_FUSE_R")) : 1; // tuning switch (default: fused)
-  if (fuse_r) {
+  // stage R variant: 2 (default) = plain loads + Riemann solvers as real functions; 1 = cp.async software pipeline;
+  // 0 = fully inlined (mhd_staged.cuh has the measurements)
+  const int staged = getenv("EK_MHD_STAGED") ? atoi(getenv("EK_MHD_STAGED")) : 2;
+  if (staged == 2) {
+    mhd_faces_edges_call_kernel<RS><<<blocks(a4, 128), 128, 0, c.stream>>>(a4);
+    c.launches += 4;
+  } else if (staged) {
+    static bool attr_done[16] = { false };
+    if (!attr_done[c.device & 15]) {
+      cudaError_t e = cudaFuncSetAttribute(mhd_faces_edges_staged_kernel<RS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STG_SMEM_BYTES);
+      if (e != cudaSuccess)
+        return e;
+      attr_done[c.device & 15] = true;
+    }
+    mhd_faces_edges_staged_kernel<RS><<<blocks(a4, STG_THREADS), STG_THREADS, STG_SMEM_BYTES, c.stream>>>(a4);
+    c.launches += 4;
+  } else if (fuse_r) {
     mhd_faces_edges_kernel<RS><<<blocks(a4, 128), 128, 0, c.stream>>>(a4);
     c.launches += 4;
   } else {

@@ -110,3 +110,15 @@ def test_mhd3d_divb_and_conservation():
     for v in (2, 3, 4):
         assert abs(s1[v] - s0[v]) <= 1e-12 * scale
     assert d0 < 1e-11 and d1 < 1e-11, (d0, d1)
+
+
+@pytest.mark.parametrize("knobs", [{"EK_MHD_STAGED": "0"}, {"EK_MHD_STAGED": "1"}, {"EK_MHD_STAGED": "2", "EK_MHD_YCHUNK": "0"},
+                                   {"EK_MHD_YCHUNK": "5", "EK_MHD_ZGROUP": "1"}, {"EK_MHD_FUSE_R": "0", "EK_MHD_STAGED": "0"}])
+def test_mhd3d_kernel_variants_agree_with_the_oracle(knobs, monkeypatch):
+    """every selectable variant of stage R (inlined / cp.async-staged / solver calls) and of the launch order
+    (flat, y-chunked, z-grouped) is held to the same one-step tolerance."""
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    p = util.make_params(dim=3, mhd=True, n=(45, 26, 19), riemann="hlld", bc=(3, 3, 1, 2, 2, 1), smallr=1e-8, smallc=1e-8,
+                         box=((0, 1.0), (0, 0.8), (0, 0.5)))
+    _check_steps(p, util.random_hydro_state(p, seed=5, mach=2.5), 2)
