@@ -144,9 +144,16 @@ static int fill_boundaries(Ctx& c, double* U)
 {
   const Grid& g = c.g;
   const int ndir = (c.p.dim == 3) ? 3 : 2;
+  if (c.halo_ready_for == U)
+    EK_CUDA(&c, cudaStreamWaitEvent(c.stream, c.ev_halo, 0));
   for (int d = 0; d < ndir; ++d) {
     const bool any_copy = c.p.bc[2 * d] == EK_BC_COPY || c.p.bc[2 * d + 1] == EK_BC_COPY;
-    if (any_copy) {
+    if (any_copy && d == 2 && c.halo_ready_for == U) {
+      // exchanged right after the end chunks of the previous step, while its middle chunks were still running
+      // (waited for above).  The x and y fills then ran over ghost planes that already held the neighbour's
+      // interior cells, which gives the same corner values as the reference order (fill x and y on both sides,
+      // then exchange): a physical fill of one (j,k) line only reads interior cells of that line.
+    } else if (any_copy) {
       int rc = comm_exchange_dir(c, U, d);
       if (rc != EK_OK)
         return rc;
@@ -165,6 +172,8 @@ static int fill_boundaries(Ctx& c, double* U)
     c.launches++;
     EK_CUDA(&c, cudaGetLastError());
   }
+  if (c.halo_ready_for == U)
+    c.halo_ready_for = nullptr; // consumed
   return EK_OK;
 }
 
@@ -223,7 +232,24 @@ static int enqueue_step(Ctx& c, int use_host_dt, double host_dt, int max_steps)
     if (rc != EK_OK)
       return rc;
     ktime_mark(c);
-    EK_CUDA(&c, launch_hydro_step(c, Uin, Uout));
+    if (c.overlap_ok) {
+      // end chunks first; their planes travel to the z neighbours (comm stream) while the middle chunks run
+      EK_CUDA(&c, cudaEventRecord(c.ev_pre, c.stream));
+      EK_CUDA(&c, launch_hydro_step(c, Uin, Uout, 1, c.stream));
+      EK_CUDA(&c, cudaEventRecord(c.ev_edge, c.stream));
+      EK_CUDA(&c, cudaStreamWaitEvent(c.aux_stream, c.ev_pre, 0));
+      EK_CUDA(&c, launch_hydro_step(c, Uin, Uout, 2, c.aux_stream));
+      EK_CUDA(&c, cudaEventRecord(c.ev_mid, c.aux_stream));
+      EK_CUDA(&c, cudaStreamWaitEvent(c.comm_stream, c.ev_edge, 0));
+      rc = comm_exchange_dir(c, Uout, 2, c.comm_stream);
+      if (rc != EK_OK)
+        return rc;
+      EK_CUDA(&c, cudaEventRecord(c.ev_halo, c.comm_stream));
+      c.halo_ready_for = Uout;
+      EK_CUDA(&c, cudaStreamWaitEvent(c.stream, c.ev_mid, 0));
+    } else {
+      EK_CUDA(&c, launch_hydro_step(c, Uin, Uout));
+    }
     ktime_mark(c);
     rc = comm_allreduce_invdt(c); // the fused reduction produced this rank's max for the next step
     if (rc != EK_OK)
@@ -282,10 +308,20 @@ int ek_create(const ek_params* params, int device, ek_ctx** out)
   CK(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
   CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
-  CK(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+  {
+    // the halo exchange must not queue behind the thousands of pending CTAs of the step kernel
+    int prio_lo = 0, prio_hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    CK(cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, prio_hi));
+  }
+  CK(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
   c->stream = c->own_stream;
   CK(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&c->ev_pre, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&c->ev_edge, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&c->ev_mid, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
   const size_t bytes = (size_t)c->state_len * sizeof(double);
   CK(cudaMalloc(&c->U[0], bytes));
   CK(cudaMalloc(&c->U[1], bytes));
@@ -318,10 +354,17 @@ int ek_destroy(ek_ctx* ctx)
   ek_comm_detach(ctx);
   for (cudaEvent_t e : c->kev) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamSynchronize(c->own_stream);
+  if (c->aux_stream) cudaStreamSynchronize(c->aux_stream);
+  if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
   cudaFree(c->U[0]); cudaFree(c->U[1]); cudaFree(c->grav); cudaFree(c->work); cudaFree(c->ts); cudaFree(c->scratch);
   if (c->ts_host) cudaFreeHost(c->ts_host);
   if (c->ev_a) cudaEventDestroy(c->ev_a);
   if (c->ev_b) cudaEventDestroy(c->ev_b);
+  if (c->ev_pre) cudaEventDestroy(c->ev_pre);
+  if (c->ev_edge) cudaEventDestroy(c->ev_edge);
+  if (c->ev_mid) cudaEventDestroy(c->ev_mid);
+  if (c->ev_halo) cudaEventDestroy(c->ev_halo);
+  if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
   delete c;
@@ -359,6 +402,7 @@ int ek_upload_state(ek_ctx* ctx, const double* U_host)
   EK_CUDA(c, cudaMemcpyAsync(c->U[1], c->U[0], bytes, cudaMemcpyDeviceToDevice, c->stream));
   c->dt_primed = false;
   c->mhd_prims_of = nullptr;
+  c->halo_ready_for = nullptr;
   EK_CUDA(c, cudaStreamSynchronize(c->stream)); // the host buffer may be pageable / reused
   return EK_OK;
 }
@@ -380,6 +424,7 @@ int ek_device_state(ek_ctx* ctx, double** dptr)
   *dptr = c->U[c->cur];
   c->dt_primed = false; // the caller may modify the state through this pointer
   c->mhd_prims_of = nullptr;
+  c->halo_ready_for = nullptr;
   return EK_OK;
 }
 
@@ -435,6 +480,8 @@ int ek_step(ek_ctx* ctx, double dt)
   if (rc != EK_OK)
     return rc;
   c->cur = 1 - c->cur;
+  if (c->halo_ready_for)
+    EK_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_halo, 0)); // later work on the stream sees the exchanged ghosts
   return EK_OK;
 }
 
@@ -454,13 +501,17 @@ int ek_run(ek_ctx* ctx, int nsteps, double t, double t_end, double* t_out, doubl
       return rc;
     c->cur = 1 - c->cur; // provisional; corrected below if the loop finished early on the device
   }
+  if (c->halo_ready_for)
+    EK_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
   EK_CUDA(c, cudaMemcpyAsync(c->ts_host, c->ts, sizeof(TimeState), cudaMemcpyDeviceToHost, c->stream));
   EK_CUDA(c, cudaStreamSynchronize(c->stream));
   const int done = c->ts_host->steps_done;
   if (((nsteps - done) & 1) != 0)
     c->cur = 1 - c->cur; // skipped steps did not flip the levels
-  if (done < nsteps)
+  if (done < nsteps) {
     c->dt_primed = false; // skipped steps consumed nothing, but be conservative
+    c->halo_ready_for = nullptr;
+  }
   if (t_out) *t_out = c->ts_host->t;
   if (dt_last_out) *dt_last_out = c->ts_host->dt;
   if (steps_done_out) *steps_done_out = done;

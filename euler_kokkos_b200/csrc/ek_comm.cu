@@ -10,6 +10,7 @@
 // straight into the state array: no pack/unpack kernels, no staging buffers.  Other directions go
 // through small packed buffers.
 #include <dlfcn.h>
+#include <cstdlib>
 #include <cstring>
 #include "ek_internal.h"
 
@@ -109,8 +110,10 @@ __global__ void __launch_bounds__(256) halo_copy_kernel(const Grid g, double* __
   }
 }
 
-int comm_exchange_dir(Ctx& c, double* U, int dir)
+int comm_exchange_dir(Ctx& c, double* U, int dir, cudaStream_t stream)
 {
+  if (!stream)
+    stream = c.stream;
   NcclApi* api = nccl_api();
   if (!api || !c.nccl_comm) {
     c.err = "boundary type EK_BC_COPY needs a communicator (ek_comm_attach)";
@@ -130,11 +133,11 @@ int comm_exchange_dir(Ctx& c, double* U, int dir)
     for (int v = 0; v < g.nbvar; ++v) {
       double* base = U + g.sv * v;
       // towards the min neighbour: my layers [gw,2gw) -> its max ghosts; I receive my max ghosts
-      if (has_min) EK_NCCL(c, api->Send(base + layer * gw, cnt, ncclDouble, nb_min, comm, c.stream));
-      if (has_max) EK_NCCL(c, api->Recv(base + layer * (n[dir] + gw), cnt, ncclDouble, nb_max, comm, c.stream));
+      if (has_min) EK_NCCL(c, api->Send(base + layer * gw, cnt, ncclDouble, nb_min, comm, stream));
+      if (has_max) EK_NCCL(c, api->Recv(base + layer * (n[dir] + gw), cnt, ncclDouble, nb_max, comm, stream));
       // towards the max neighbour: my layers [n,n+gw) -> its min ghosts; I receive my min ghosts
-      if (has_max) EK_NCCL(c, api->Send(base + layer * n[dir], cnt, ncclDouble, nb_max, comm, c.stream));
-      if (has_min) EK_NCCL(c, api->Recv(base, cnt, ncclDouble, nb_min, comm, c.stream));
+      if (has_max) EK_NCCL(c, api->Send(base + layer * n[dir], cnt, ncclDouble, nb_max, comm, stream));
+      if (has_min) EK_NCCL(c, api->Recv(base, cnt, ncclDouble, nb_min, comm, stream));
     }
     EK_NCCL(c, api->GroupEnd());
     return EK_OK;
@@ -152,16 +155,16 @@ int comm_exchange_dir(Ctx& c, double* U, int dir)
   }
   long long nbl = (long long)((cnt + 255) / 256);
   if (nbl > (long long)c.sm_count * 8) nbl = (long long)c.sm_count * 8;
-  if (has_min) { halo_copy_kernel<true><<<(int)nbl, 256, 0, c.stream>>>(g, U, c.halo_send[2 * dir], dir, gw); c.launches++; }
-  if (has_max) { halo_copy_kernel<true><<<(int)nbl, 256, 0, c.stream>>>(g, U, c.halo_send[2 * dir + 1], dir, n[dir]); c.launches++; }
+  if (has_min) { halo_copy_kernel<true><<<(int)nbl, 256, 0, stream>>>(g, U, c.halo_send[2 * dir], dir, gw); c.launches++; }
+  if (has_max) { halo_copy_kernel<true><<<(int)nbl, 256, 0, stream>>>(g, U, c.halo_send[2 * dir + 1], dir, n[dir]); c.launches++; }
   EK_NCCL(c, api->GroupStart());
-  if (has_min) EK_NCCL(c, api->Send(c.halo_send[2 * dir], cnt, ncclDouble, nb_min, comm, c.stream));
-  if (has_max) EK_NCCL(c, api->Recv(c.halo_recv[2 * dir + 1], cnt, ncclDouble, nb_max, comm, c.stream));
-  if (has_max) EK_NCCL(c, api->Send(c.halo_send[2 * dir + 1], cnt, ncclDouble, nb_max, comm, c.stream));
-  if (has_min) EK_NCCL(c, api->Recv(c.halo_recv[2 * dir], cnt, ncclDouble, nb_min, comm, c.stream));
+  if (has_min) EK_NCCL(c, api->Send(c.halo_send[2 * dir], cnt, ncclDouble, nb_min, comm, stream));
+  if (has_max) EK_NCCL(c, api->Recv(c.halo_recv[2 * dir + 1], cnt, ncclDouble, nb_max, comm, stream));
+  if (has_max) EK_NCCL(c, api->Send(c.halo_send[2 * dir + 1], cnt, ncclDouble, nb_max, comm, stream));
+  if (has_min) EK_NCCL(c, api->Recv(c.halo_recv[2 * dir], cnt, ncclDouble, nb_min, comm, stream));
   EK_NCCL(c, api->GroupEnd());
-  if (has_min) { halo_copy_kernel<false><<<(int)nbl, 256, 0, c.stream>>>(g, U, c.halo_recv[2 * dir], dir, 0); c.launches++; }
-  if (has_max) { halo_copy_kernel<false><<<(int)nbl, 256, 0, c.stream>>>(g, U, c.halo_recv[2 * dir + 1], dir, n[dir] + gw); c.launches++; }
+  if (has_min) { halo_copy_kernel<false><<<(int)nbl, 256, 0, stream>>>(g, U, c.halo_recv[2 * dir], dir, 0); c.launches++; }
+  if (has_max) { halo_copy_kernel<false><<<(int)nbl, 256, 0, stream>>>(g, U, c.halo_recv[2 * dir + 1], dir, n[dir] + gw); c.launches++; }
   if (cudaGetLastError() != cudaSuccess) {
     c.err = "halo pack/unpack launch failed";
     return EK_ERR_CUDA;
@@ -226,6 +229,23 @@ int ek_comm_attach(ek_ctx* ctx, const void* id, int rank, int nranks, const int3
     }
   }
   c->dt_primed = false;
+  c->halo_ready_for = nullptr;
+  // Overlap of the z-halo exchange with the interior of the step: hydro 3-D, slabs along z only, and a z extent
+  // that can be cut into end + middle chunks.  Every rank must take the same decision (it changes the order of
+  // the NCCL calls), hence the min-reduction.
+  {
+    const bool want = !(getenv("EK_HALO_OVERLAP") && atoi(getenv("EK_HALO_OVERLAP")) == 0);
+    const bool zcopy = c->p.bc[4] == EK_BC_COPY || c->p.bc[5] == EK_BC_COPY;
+    const bool xycopy = c->p.bc[0] == EK_BC_COPY || c->p.bc[1] == EK_BC_COPY || c->p.bc[2] == EK_BC_COPY || c->p.bc[3] == EK_BC_COPY;
+    double ok = (want && !c->p.mhd && c->p.dim == 3 && zcopy && !xycopy && hydro_z_splittable(*c)) ? 1.0 : 0.0;
+    if (nranks > 1) {
+      if (cudaMemcpyAsync(c->scratch, &ok, sizeof(double), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { c->err = "overlap probe: H2D failed"; return EK_ERR_CUDA; }
+      EK_NCCL(*c, api->AllReduce(c->scratch, c->scratch, 1, ncclDouble, ncclMin, comm, c->stream));
+      if (cudaMemcpyAsync(&ok, c->scratch, sizeof(double), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+          cudaStreamSynchronize(c->stream) != cudaSuccess) { c->err = "overlap probe: D2H failed"; return EK_ERR_CUDA; }
+    }
+    c->overlap_ok = ok > 0.5;
+  }
   return EK_OK;
 }
 
@@ -244,6 +264,8 @@ int ek_comm_detach(ek_ctx* ctx)
   }
   c->nranks = 1;
   c->rank = 0;
+  c->overlap_ok = false;
+  c->halo_ready_for = nullptr;
   return EK_OK;
 }
 

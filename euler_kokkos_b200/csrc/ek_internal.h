@@ -16,8 +16,14 @@ struct Ctx {
   int device = 0;
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;      // own_stream or caller-provided
-  cudaStream_t comm_stream = nullptr; // halo exchange
+  cudaStream_t comm_stream = nullptr; // halo exchange (high priority)
+  cudaStream_t aux_stream = nullptr;  // middle z-chunks of a split step (runs beside the halo exchange)
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  cudaEvent_t ev_pre = nullptr, ev_edge = nullptr, ev_mid = nullptr, ev_halo = nullptr;
+  // overlap of the z-halo exchange with the interior of the step (hydro 3-D, z slabs): the ghost planes of
+  // level `halo_ready_for` have already been exchanged (on comm_stream, completion = ev_halo)
+  bool overlap_ok = false;              // decided at ek_comm_attach, identical on every rank
+  const double* halo_ready_for = nullptr;
   double* U[2] = { nullptr, nullptr }; // ping-pong levels
   int cur = 0;                         // index of the current level
   double* grav = nullptr;
@@ -56,14 +62,15 @@ inline void ktime_mark(Ctx& c)
 }
 
 // hydro_launch.cu
-cudaError_t launch_hydro_step(Ctx& c, const double* Uin, double* Uout);
+cudaError_t launch_hydro_step(Ctx& c, const double* Uin, double* Uout, int part = 0, cudaStream_t stream = nullptr);
+bool hydro_z_splittable(const Ctx& c);
 cudaError_t launch_hydro_invdt(Ctx& c, const double* U);
 // mhd_launch.cu
 cudaError_t launch_mhd_step(Ctx& c, const double* Uin, double* Uout);
 cudaError_t launch_mhd_invdt(Ctx& c, const double* U);
 size_t mhd_work_bytes(const Grid& g);
 // ek_comm.cu
-int comm_exchange_dir(Ctx& c, double* U, int dir);       // halo exchange along one direction
+int comm_exchange_dir(Ctx& c, double* U, int dir, cudaStream_t stream = nullptr); // halo exchange along one direction
 int comm_allreduce_invdt(Ctx& c);                        // max over ranks of ts->invdt_bits
 int comm_allreduce_sum(Ctx& c, double* dev_vals, int n); // diagnostics
 int comm_allreduce_max(Ctx& c, double* dev_vals, int n);

@@ -46,6 +46,8 @@ struct HydroArgs {
   const double* __restrict__ grav; // [DIM][k][j][i] or nullptr
   TimeState* ts;
   int zchunk; // planes per CTA along z (3-D)
+  int zfirst; // z-chunk of blockIdx.z = 0 ...
+  int zstep;  // ... and chunk stride per blockIdx.z (lets one launch take the two end chunks, another the middle ones)
 };
 
 template <int DIM, int RS, int TY, bool GRAV>
@@ -97,7 +99,7 @@ __global__ void __launch_bounds__(32 * (TY + 4), 1) hydro_step_kernel(const Hydr
 
   int kbeg = 0, kend = 1;
   if constexpr (DIM == 3) {
-    kbeg = g.gw + blockIdx.z * a.zchunk;
+    kbeg = g.gw + (a.zfirst + (int)blockIdx.z * a.zstep) * a.zchunk;
     kend = min(kbeg + a.zchunk, g.nz + g.gw);
   }
   double invdt = 0.0;

@@ -15,13 +15,13 @@ constexpr int TY = EK_HYDRO_TY;
 
 // z-chunk length: enough CTAs to fill whole waves over the SMs, long enough to amortise the
 // 3-plane pipeline warm-up of every chunk.
-static int pick_zchunk(int nz, long long xy_ctas, int sm_count)
+static int pick_zchunk(int nz, long long xy_ctas, int sm_count, int min_chunks = 1, int min_len = 8)
 {
   int best = nz;
   double best_cost = 1e300;
-  for (int nchunk = 1; nchunk <= nz; ++nchunk) {
+  for (int nchunk = min_chunks; nchunk <= nz; ++nchunk) {
     const int zc = (nz + nchunk - 1) / nchunk;
-    if (zc < 8 && nchunk > 1)
+    if (zc < min_len && nchunk > min_chunks)
       break;
     const long long real_chunks = (nz + zc - 1) / zc;
     const long long ctas = xy_ctas * real_chunks;
@@ -37,8 +37,39 @@ static int pick_zchunk(int nz, long long xy_ctas, int sm_count)
   return best;
 }
 
+// z-chunking of the 3-D step.  With split = true the chunks are laid out so that the launch can be cut in two:
+// the two END chunks (they produce the planes the z neighbours need as ghosts) and the MIDDLE chunks.
+struct ZPlan {
+  int zchunk, nchunk;
+  bool splittable;
+};
+static ZPlan z_plan(const Ctx& c, long long xy_ctas, bool want_split)
+{
+  ZPlan z;
+  const int nz = c.g.nz, gw = c.g.gw;
+  z.zchunk = pick_zchunk(nz, xy_ctas, c.sm_count);
+  z.nchunk = (nz + z.zchunk - 1) / z.zchunk;
+  z.splittable = false;
+  if (!want_split)
+    return z;
+  const int zc = (z.nchunk >= 3) ? z.zchunk : pick_zchunk(nz, xy_ctas, c.sm_count, 3, gw);
+  const int nc = (nz + zc - 1) / zc;
+  const int last = nz - (nc - 1) * zc;
+  if (nc >= 3 && zc >= gw && last >= gw) {
+    z.zchunk = zc;
+    z.nchunk = nc;
+    z.splittable = true;
+  }
+  return z;
+}
+
+static long long hydro_xy_ctas(const Grid& g) { return (long long)((g.nx + HTX - 1) / HTX) * ((g.ny + TY - 1) / TY); }
+
+bool hydro_z_splittable(const Ctx& c) { return c.p.dim == 3 && z_plan(c, hydro_xy_ctas(c.g), true).splittable; }
+
+// part: 0 = every chunk, 1 = the two end chunks, 2 = the middle chunks (1 and 2 only when splittable)
 template <int DIM, int RS, bool GRAV>
-static cudaError_t launch_one(Ctx& c, const double* Uin, double* Uout)
+static cudaError_t launch_one(Ctx& c, const double* Uin, double* Uout, int part, cudaStream_t stream)
 {
   using Smem = HydroSmem<DIM, TY>;
   auto kern = hydro_step_kernel<DIM, RS, TY, GRAV>;
@@ -59,38 +90,52 @@ static cudaError_t launch_one(Ctx& c, const double* Uin, double* Uout)
   dim3 block(32, TY + 4, 1);
   dim3 grid((c.g.nx + HTX - 1) / HTX, (c.g.ny + TY - 1) / TY, 1);
   a.zchunk = 1;
+  a.zfirst = 0;
+  a.zstep = 1;
   if (DIM == 3) {
-    a.zchunk = pick_zchunk(c.g.nz, (long long)grid.x * grid.y, c.sm_count);
-    grid.z = (c.g.nz + a.zchunk - 1) / a.zchunk;
+    const ZPlan z = z_plan(c, (long long)grid.x * grid.y, part != 0);
+    if (part != 0 && !z.splittable)
+      return cudaErrorInvalidValue;
+    a.zchunk = z.zchunk;
+    grid.z = z.nchunk;
+    if (part == 1) {
+      a.zstep = z.nchunk - 1;
+      grid.z = 2;
+    } else if (part == 2) {
+      a.zfirst = 1;
+      grid.z = z.nchunk - 2;
+    }
   }
-  kern<<<grid, block, smem, c.stream>>>(a);
+  kern<<<grid, block, smem, stream>>>(a);
   c.launches++;
   return cudaGetLastError();
 }
 
 template <int DIM, int RS>
-static cudaError_t launch_grav(Ctx& c, const double* Uin, double* Uout)
+static cudaError_t launch_grav(Ctx& c, const double* Uin, double* Uout, int part, cudaStream_t stream)
 {
   if (c.p.gravity_enabled)
-    return launch_one<DIM, RS, true>(c, Uin, Uout);
-  return launch_one<DIM, RS, false>(c, Uin, Uout);
+    return launch_one<DIM, RS, true>(c, Uin, Uout, part, stream);
+  return launch_one<DIM, RS, false>(c, Uin, Uout, part, stream);
 }
 
-cudaError_t launch_hydro_step(Ctx& c, const double* Uin, double* Uout)
+cudaError_t launch_hydro_step(Ctx& c, const double* Uin, double* Uout, int part, cudaStream_t stream)
 {
+  if (!stream)
+    stream = c.stream;
   if (c.p.dim == 3) {
     switch (c.p.riemann) {
-      case RIEMANN_HLLC: return launch_grav<3, RIEMANN_HLLC>(c, Uin, Uout);
-      case RIEMANN_APPROX: return launch_grav<3, RIEMANN_APPROX>(c, Uin, Uout);
-      case RIEMANN_LLF: return launch_grav<3, RIEMANN_LLF>(c, Uin, Uout);
+      case RIEMANN_HLLC: return launch_grav<3, RIEMANN_HLLC>(c, Uin, Uout, part, stream);
+      case RIEMANN_APPROX: return launch_grav<3, RIEMANN_APPROX>(c, Uin, Uout, part, stream);
+      case RIEMANN_LLF: return launch_grav<3, RIEMANN_LLF>(c, Uin, Uout, part, stream);
       default: return cudaErrorInvalidValue;
     }
   }
   switch (c.p.riemann) {
-    case RIEMANN_HLLC: return launch_grav<2, RIEMANN_HLLC>(c, Uin, Uout);
-    case RIEMANN_APPROX: return launch_grav<2, RIEMANN_APPROX>(c, Uin, Uout);
-    case RIEMANN_LLF: return launch_grav<2, RIEMANN_LLF>(c, Uin, Uout);
-    case RIEMANN_HLL: return launch_grav<2, RIEMANN_HLL>(c, Uin, Uout);
+    case RIEMANN_HLLC: return launch_grav<2, RIEMANN_HLLC>(c, Uin, Uout, part, stream);
+    case RIEMANN_APPROX: return launch_grav<2, RIEMANN_APPROX>(c, Uin, Uout, part, stream);
+    case RIEMANN_LLF: return launch_grav<2, RIEMANN_LLF>(c, Uin, Uout, part, stream);
+    case RIEMANN_HLL: return launch_grav<2, RIEMANN_HLL>(c, Uin, Uout, part, stream);
     default: return cudaErrorInvalidValue;
   }
 }

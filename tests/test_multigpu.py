@@ -74,8 +74,18 @@ def _run_case(ini_name, overrides_local, nz_local, world, nsteps, tmp_path, tol)
     assert err <= tol, err
 
 
-def test_hydro3d_two_slabs_match_single_domain(tmp_path):
+@pytest.mark.parametrize("overlap", ["1", "0"])
+def test_hydro3d_two_slabs_match_single_domain(tmp_path, monkeypatch, overlap):
+    """overlap=1: the z-halo exchange of step n+1 runs beside the middle z-chunks of step n (ek_api.cu enqueue_step);
+    overlap=0: exchange at the start of the step, as the reference's MPI path does.  Same answer either way."""
+    monkeypatch.setenv("EK_HALO_OVERLAP", overlap)
     _run_case("test_implode_3D.ini", {"mesh.nx": 40, "mesh.ny": 36}, 20, 2, 10, tmp_path, 1e-13)
+
+
+def test_hydro3d_two_slabs_periodic_z_with_gravity(tmp_path):
+    """both z faces of both slabs are halo faces (periodic wrap), gravity + approx solver (config 4 physics)"""
+    _run_case("test_rayleigh_taylor_3d.ini", {"mesh.nx": 24, "mesh.ny": 20, "mesh.boundary_type_zmin": 3, "mesh.boundary_type_zmax": 3},
+              16, 2, 6, tmp_path, 1e-13)
 
 
 def test_mhd3d_two_slabs_periodic_match_single_domain(tmp_path):
