@@ -41,6 +41,20 @@ WORKLOADS = {
 }
 
 
+def recorded_traffic(fam, p):
+    """per-launch DRAM traffic of the dominant kernel from the committed ncu capture (profiles/traffic.json), or None
+    when this workload/size has not been captured"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            d = json.load(f)
+        key = f"{'mhd' if fam == 'mhd' else fam.replace('_grav', '')}@{p.nx}"
+        if p.nx == p.ny == p.nz and key in d and not (fam.endswith("_grav")):
+            return d[key]
+    except Exception:
+        pass
+    return None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -224,6 +238,7 @@ def run_ours(args):
         bpc = ALGO_BYTES[w["fam"]]
         k_avg_ms = kms / max(kn, 1)
         achieved = bpc * cells_local / (k_avg_ms * 1e-3) / 1e9 if kn else None
+        rec = recorded_traffic(w["fam"], p)
         line = {
             "metric": "cell-updates/s (FP64)", "value": value, "unit": "cell-updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -232,7 +247,10 @@ def run_ours(args):
                        "l2": "inputs (2 x %.1f GB state) larger than L2; no flush needed" % (nbytes / 1e9),
                        "decomposition": "1 z-slab per GPU, NCCL halos" if world > 1 else "single domain"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                         "traffic": None, "peak_source": peak_src, "kernel": case.kernel_name(), "kernel_ms": k_avg_ms,
+                         "traffic": (rec["traffic_bytes"] / 1e9) if rec else None, "traffic_unit": "GB per launch (ncu dram bytes read+write)",
+                         "traffic_source": rec["source"] if rec else None, "algorithmic_gb_per_launch": bpc * cells_local / 1e9,
+                         "fp64_pipe_active_frac_ncu": rec.get("fp64_pipe_active_frac") if rec else None,
+                         "fp64_peak_thread_inst_per_s": 18.4e12, "peak_source": peak_src, "kernel": case.kernel_name(), "kernel_ms": k_avg_ms,
                          "kernel_share_of_step": (kms / ms) if ms else None, "algorithmic_bytes_per_cell": bpc},
             "e2e": {"value": e2e_value, "unit": "cell-updates/s", "h2d_bytes_per_step": nbytes / args.steps,
                     "d2h_bytes_per_step": nbytes / args.steps + 8, "what": "upload(pinned) + K x {compute_dt -> host, step} + download(pinned)",
