@@ -1,4 +1,5 @@
 #include "InitConditions.h"
+#include "InitGeo.h"
 
 #include <cmath>
 #include <cstdio>
@@ -8,36 +9,6 @@
 namespace euler_b200 {
 
 namespace {
-
-struct Geo {
-  int dim, gw, nx, ny, nz, isize, jsize, ksize;
-  int i_mpi, j_mpi, k_mpi;
-  size_t sj, sk, sv;
-  double xmin, xmax, ymin, ymax, zmin, zmax, dx, dy, dz;
-  explicit Geo(const HydroParams& p)
-  {
-    dim = p.dimType; gw = p.ghostWidth; nx = p.nx; ny = p.ny; nz = p.nz;
-    isize = p.isize; jsize = p.jsize; ksize = (dim == 3) ? p.ksize : 1;
-    i_mpi = p.myMpiPos[0]; j_mpi = p.myMpiPos[1]; k_mpi = p.myMpiPos[2];
-    sj = isize; sk = (size_t)isize * jsize; sv = sk * ksize;
-    xmin = p.xmin; xmax = p.xmax; ymin = p.ymin; ymax = p.ymax; zmin = p.zmin; zmax = p.zmax;
-    dx = p.dx; dy = p.dy; dz = p.dz;
-  }
-  double x(int i) const { return xmin + dx / 2 + (i + nx * i_mpi - gw) * dx; }
-  double y(int j) const { return ymin + dy / 2 + (j + ny * j_mpi - gw) * dy; }
-  double z(int k) const { return zmin + dz / 2 + (k + nz * k_mpi - gw) * dz; }
-  size_t at(int i, int j, int k) const { return (size_t)i + sj * j + sk * k; }
-};
-
-template <class F>
-void for_each_cell(const Geo& g, F f)
-{
-#pragma omp parallel for schedule(static)
-  for (int k = 0; k < g.ksize; ++k)
-    for (int j = 0; j < g.jsize; ++j)
-      for (int i = 0; i < g.isize; ++i)
-        f(i, j, k);
-}
 
 // ---- implode: ImplodeParams.h, InitImplodeFunctor{2D,3D} ----------------------------------------
 void init_implode(const HydroParams& p, const ConfigMap& cm, double* U)
@@ -272,10 +243,10 @@ bool init_problem(const std::string& problem, const HydroParams& params, const C
     if (problem == "implode") { init_implode(params, configMap, U); return true; }
     if (problem == "blast") { init_blast(params, configMap, U); return true; }
     if (problem == "rayleigh_taylor") { init_rayleigh_taylor(params, configMap, U, grav); return true; }
-    if (problem == "kelvin_helmholtz" || problem == "gresho_vortex" || problem == "four_quadrant" || problem == "isentropic_vortex") {
-      std::cerr << "[euler_b200] initial condition '" << problem << "' is not implemented (outside the hot-path scope)\n";
-      return false;
-    }
+    if (problem == "kelvin_helmholtz") return init_kelvin_helmholtz(params, configMap, U);
+    if (problem == "gresho_vortex") return init_gresho_vortex(params, configMap, U);
+    if (problem == "four_quadrant") return init_four_quadrant(params, configMap, U);
+    if (problem == "isentropic_vortex") return init_isentropic_vortex(params, configMap, U);
     // SolverHydroMuscl.cpp:131-137: unknown problem -> implode
     std::cout << "Problem : " << problem << " is not recognized / implemented." << std::endl;
     std::cout << "Use default - implode" << std::endl;
@@ -283,11 +254,12 @@ bool init_problem(const std::string& problem, const HydroParams& params, const C
     return true;
   }
   if (problem == "orszag_tang") { init_orszag_tang(params, configMap, U); return true; }
-  if (problem == "implode" || problem == "blast" || problem == "brio-wu" || problem == "kelvin_helmholtz" || problem == "rotor" ||
-      problem == "field_loop" || problem == "field loop") {
-    std::cerr << "[euler_b200] MHD initial condition '" << problem << "' is not implemented (outside the hot-path scope)\n";
-    return false;
-  }
+  if (problem == "blast") return init_mhd_blast(params, configMap, U);
+  if (problem == "implode") return init_mhd_implode(params, configMap, U);
+  if (problem == "brio-wu") return init_mhd_brio_wu(params, configMap, U);
+  if (problem == "kelvin_helmholtz") return init_mhd_kelvin_helmholtz(params, configMap, U);
+  if (problem == "rotor") return init_mhd_rotor(params, configMap, U);
+  if (problem == "field_loop" || problem == "field loop") return init_mhd_field_loop(params, configMap, U);
   // SolverMHDMuscl.h:706-713: unknown problem -> Orszag-Tang
   std::cout << "Problem : " << problem << " is not recognized / implemented." << std::endl;
   std::cout << "Use default - Orszag-Tang vortex" << std::endl;

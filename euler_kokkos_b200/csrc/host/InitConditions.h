@@ -7,9 +7,9 @@
 //   orszag_tang      src/muscl/MHDInitFunctors2D.h:345-482, MHDInitFunctors3D.h:376-555
 // plus the parameter structs in src/shared/problems/*.h.  Problem dispatch follows
 // SolverHydroMuscl<dim>::init (src/muscl/SolverHydroMuscl.cpp:80-207) and SolverMHDMuscl<dim>::init
-// (src/muscl/SolverMHDMuscl.h:640-716).  Other problems of the reference (Kelvin-Helmholtz, Gresho,
-// four-quadrant, isentropic vortex, Brio-Wu, rotor, field loop, MHD blast/implode) are not part of
-// the hot-path scope and are rejected with a message.
+// (src/muscl/SolverMHDMuscl.h:640-716).  The other problems of the reference (Kelvin-Helmholtz, Gresho,
+// four-quadrant, isentropic vortex, Brio-Wu, rotor, field loop, MHD blast/implode/KH) live in
+// InitConditionsMore.cpp.
 #pragma once
 #include <string>
 

@@ -30,6 +30,7 @@ from oracle import oracle_lib as O  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
+R = "/root/reference/settings/"
 # name -> (settings file, overrides, number of steps, steps kept)
 CASES = {
     "implode2d_hllc": ("test_implode_2D.ini", {"mesh.nx": 48, "mesh.ny": 24}, 8, (1, 2, 8)),
@@ -58,6 +59,20 @@ CASES = {
                             "mesh.boundary_type_xmin": 1, "mesh.boundary_type_xmax": 2, "mesh.boundary_type_ymin": 3,
                             "mesh.boundary_type_ymax": 3}, 10, (1, 5, 10)),
     "ot3d_llf": ("test_mhd_orszag_tang_3D.ini", {"mesh.nx": 16, "mesh.ny": 12, "mesh.nz": 8, "hydro.riemann": "llf"}, 3, (1, 3)),
+    # ---- the remaining problems of the reference, from its own settings files ----------------
+    "fourquad2d_hllc": (R + "test_four_quadrant_2D.ini", {"mesh.nx": 40, "mesh.ny": 36}, 6, (1, 6)),
+    "fourquad3d_hllc": (R + "test_four_quadrant_3D.ini", {"mesh.nx": 16, "mesh.ny": 14, "mesh.nz": 12}, 4, (1, 4)),
+    "gresho2d_hllc": (R + "test_muscl_gresho_vortex_2D.ini", {"mesh.nx": 32, "mesh.ny": 32}, 4, (1, 4)),
+    "isentropic2d_hllc": (R + "test_muscl_isentropic_vortex_2d.ini", {"mesh.nx": 32, "mesh.ny": 28}, 4, (1, 4)),
+    "kh2d_hllc": (R + "test_muscl_kelvin_helmholtz_2D.ini", {"mesh.nx": 32, "mesh.ny": 32}, 4, (1, 4)),
+    "kh3d_hllc": (R + "test_muscl_kelvin_helmholtz_3D.ini", {"mesh.nx": 16, "mesh.ny": 16, "mesh.nz": 16}, 3, (1, 3)),
+    "mhdkh2d_hlld": (R + "test_muscl_kelvin_helmholtz_2D_mhd.ini", {"mesh.nx": 32, "mesh.ny": 32}, 4, (1, 4)),
+    "briowu2d_x_hlld": (R + "test_mhd_brio_wu_2d_x.ini", {"mesh.nx": 64, "mesh.ny": 8, "other.implementationversion": 0}, 8, (1, 8)),
+    "briowu2d_y_hlld": (R + "test_mhd_brio_wu_2d_y.ini", {"mesh.nx": 8, "mesh.ny": 48, "other.implementationversion": 0}, 6, (1, 6)),
+    "briowu3d_z_hlld": (R + "test_mhd_brio_wu_3d_z.ini", {"mesh.nx": 8, "mesh.ny": 8, "mesh.nz": 48, "other.implementationversion": 0}, 6, (1, 6)),
+    "rotor2d_hlld": (R + "test_mhd_rotor.ini", {"mesh.nx": 40, "mesh.ny": 40}, 5, (1, 5)),
+    "fieldloop2d_hlld": (R + "mhd_fieldloop2d.ini", {"mesh.nx": 32, "mesh.ny": 20, "hydro.problem": "field_loop"}, 5, (1, 5)),
+    "fieldloop3d_hlld": (R + "mhd_fieldloop3d.ini", {"mesh.nx": 24, "mesh.ny": 12, "mesh.nz": 12, "hydro.problem": "field_loop"}, 4, (1, 4)),
 }
 
 
