@@ -7,6 +7,56 @@
 
 namespace euler_b200 {
 
+// .pvti header of a decomposed run: whole extent, one <Piece> per rank (rank -> Cartesian coordinates as
+// HydroParams::setup_mpi, row-major like MPI_Cart_create)
+void write_pvti_header(const std::string& headerFilename, const std::string& outputPrefix, const HydroParams& params, int nbvar,
+                       const std::map<int, std::string>& varNames, int iStep)
+{
+  const bool three_d = params.dimType == THREE_D;
+  const int nx = params.nx, ny = params.ny, nz = three_d ? params.nz : 0;
+  const int mx = params.mx, my = params.my, mz = three_d ? params.mz : 0;
+  std::ostringstream stepNum;
+  stepNum.width(7);
+  stepNum.fill('0');
+  stepNum << iStep;
+  std::ofstream out(headerFilename.c_str(), std::ios_base::out);
+  if (!out)
+    return;
+  out << "<?xml version=\"1.0\"?>\n";
+  out << "<VTKFile type=\"PImageData\" version=\"1.0\" byte_order=\"LittleEndian\" header_type=\"UInt64\">\n";
+  out << "  <PImageData WholeExtent=\"" << 0 << " " << mx * nx << " " << 0 << " " << my * ny << " " << 0 << " " << mz * nz
+      << "\" GhostLevel=\"0\" Origin=\"" << params.xmin << " " << params.ymin << " " << params.zmin << "\" Spacing=\"" << params.dx << " "
+      << params.dy << " " << (three_d ? params.dz : 0.0) << "\">\n";
+  out << "    <PCellData Scalars=\"Scalars_\">\n";
+  for (int iVar = 0; iVar < nbvar; ++iVar)
+    out << "      <PDataArray type=\"Float64\" Name=\"" << varNames.at(iVar) << "\"/>\n";
+  out << "    </PCellData>\n";
+  for (int r = 0; r < params.nProcs; ++r) {
+    std::ostringstream rankNum;
+    rankNum.width(5);
+    rankNum.fill('0');
+    rankNum << r;
+    const std::string piece = outputPrefix + "_time" + stepNum.str() + "_mpi" + rankNum.str() + ".vti";
+    int cx, cy, cz = 0;
+    if (three_d) {
+      cx = r / (my * params.mz);
+      cy = (r / params.mz) % my;
+      cz = r % params.mz;
+    } else {
+      cx = r / my;
+      cy = r % my;
+    }
+    out << "    <Piece Extent=\"" << cx * nx << " " << cx * nx + nx << " " << cy * ny << " " << cy * ny + ny << " ";
+    if (three_d)
+      out << cz * nz << " " << cz * nz + nz << " ";
+    else
+      out << 0 << " " << 1;
+    out << "\" Source=\"" << piece << "\"/>\n";
+  }
+  out << "  </PImageData>\n";
+  out << "</VTKFile>\n";
+}
+
 std::string save_vti(const double* U, const HydroParams& params, const ConfigMap& configMap, int nbvar,
                      const std::map<int, std::string>& variables_names, int iStep)
 {
@@ -18,35 +68,41 @@ std::string save_vti(const double* U, const HydroParams& params, const ConfigMap
 
   std::string outputDir = configMap.getString("output", "outputDir", "./");
   std::string outputPrefix = configMap.getString("output", "outputPrefix", "output");
-  if (params.nProcs > 1) {
-    char buf[32];
-    snprintf(buf, sizeof(buf), "_rank%05d", params.myRank);
-    outputPrefix += buf;
-  }
   std::ostringstream stepNum;
   stepNum.width(7);
   stepNum.fill('0');
   stepNum << iStep;
-  const std::string filename = outputDir + "/" + outputPrefix + "_" + stepNum.str() + ".vti";
+  // decomposed runs: one piece per rank + a .pvti header written by rank 0, with the reference's file names and
+  // global cell extents (save_VTK_{2D,3D}_mpi + write_pvti_header, src/utils/io/IO_VTK.cpp:415-1011)
+  const bool pieces = params.nProcs > 1;
+  std::string filename = outputDir + "/" + outputPrefix + "_" + stepNum.str() + ".vti";
+  if (pieces) {
+    std::ostringstream rankNum;
+    rankNum.width(5);
+    rankNum.fill('0');
+    rankNum << params.myRank;
+    filename = outputDir + "/" + outputPrefix + "_time" + stepNum.str() + "_mpi" + rankNum.str() + ".vti";
+    if (params.myRank == 0)
+      write_pvti_header(outputDir + "/" + outputPrefix + "_time" + stepNum.str() + ".pvti", outputPrefix, params, nbvar, variables_names, iStep);
+  }
 
   std::ofstream out(filename.c_str(), std::ios_base::out | std::ios_base::binary);
   if (!out)
     return std::string();
-  // sub-domain origin (the reference writes the global xmin and relies on .pvti extents)
-  const double ox = params.xmin + params.myMpiPos[0] * nx * params.dx;
-  const double oy = params.ymin + params.myMpiPos[1] * ny * params.dy;
-  const double oz = params.zmin + params.myMpiPos[2] * nz * params.dz;
-  out << "<VTKFile type=\"ImageData\" version=\"0.1\" byte_order=\"LittleEndian\" header_type=\"UInt64\">\n";
+  // global cell extents of this piece; the origin is the global one (the pieces are placed by their extents)
+  const int x0 = params.myMpiPos[0] * nx, y0 = params.myMpiPos[1] * ny, z0 = three_d ? params.myMpiPos[2] * nz : 0;
+  const double ox = params.xmin, oy = params.ymin, oz = params.zmin;
+  out << "<VTKFile type=\"ImageData\" version=\"" << (pieces ? "1.0" : "0.1") << "\" byte_order=\"LittleEndian\" header_type=\"UInt64\">\n";
   if (three_d) {
-    out << "  <ImageData WholeExtent=\"" << 0 << " " << nx << " " << 0 << " " << ny << " " << 0 << " " << nz << "\" "
+    out << "  <ImageData WholeExtent=\"" << x0 << " " << x0 + nx << " " << y0 << " " << y0 + ny << " " << z0 << " " << z0 + nz << "\" "
         << "Origin=\"" << ox << " " << oy << " " << oz << "\" "
         << "Spacing=\"" << params.dx << " " << params.dy << " " << params.dz << "\">\n";
-    out << "  <Piece Extent=\"" << 0 << " " << nx << " " << 0 << " " << ny << " " << 0 << " " << nz << " " << "\">\n";
+    out << "  <Piece Extent=\"" << x0 << " " << x0 + nx << " " << y0 << " " << y0 + ny << " " << z0 << " " << z0 + nz << " " << "\">\n";
   } else {
-    out << "  <ImageData WholeExtent=\"" << 0 << " " << nx << " " << 0 << " " << ny << " " << 0 << " " << 0 << "\" "
+    out << "  <ImageData WholeExtent=\"" << x0 << " " << x0 + nx << " " << y0 << " " << y0 + ny << " " << 0 << " " << 0 << "\" "
         << "Origin=\"" << ox << " " << oy << " " << 0 << "\" "
         << "Spacing=\"" << params.dx << " " << params.dy << " " << 0 << "\">\n";
-    out << "  <Piece Extent=\"" << 0 << " " << nx << " " << 0 << " " << ny << " " << 0 << " " << 0 << " " << "\">\n";
+    out << "  <Piece Extent=\"" << x0 << " " << x0 + nx << " " << y0 << " " << y0 + ny << " " << 0 << " " << 0 << " " << "\">\n";
   }
   out << "    <PointData>\n";
   out << "    </PointData>\n";

@@ -9,8 +9,11 @@
 
 namespace euler_b200 {
 
-//! U: ghosted SoA state [var][k][j][i]; writes <outputDir>/<outputPrefix>_%07d.vti
-//! (multi-rank runs append _rank%05d to the prefix; the .pvti collection file is not written)
+//! U: ghosted SoA state [var][k][j][i]; writes <outputDir>/<outputPrefix>_%07d.vti.  Decomposed runs write one piece
+//! per rank, <outputPrefix>_time%07d_mpi%05d.vti with global cell extents, and rank 0 adds the
+//! <outputPrefix>_time%07d.pvti header (the reference's save_VTK_*_mpi / write_pvti_header, IO_VTK.cpp:415-1011).
+void write_pvti_header(const std::string& headerFilename, const std::string& outputPrefix, const HydroParams& params, int nbvar,
+                       const std::map<int, std::string>& varNames, int iStep);
 std::string save_vti(const double* U, const HydroParams& params, const ConfigMap& configMap, int nbvar,
                      const std::map<int, std::string>& variables_names, int iStep);
 

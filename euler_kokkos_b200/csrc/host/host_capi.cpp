@@ -6,6 +6,7 @@
 
 #include "ConfigMap.h"
 #include "HydroParams.h"
+#include "IO_VTK.h"
 #include "InitConditions.h"
 #include "SolverFactory.h"
 
@@ -90,6 +91,25 @@ int ekh_case_write_ini(void* h, const char* path)
   std::ofstream f(path);
   if (!f) return 2;
   f << static_cast<HostCase*>(h)->configMap.toIni();
+  return 0;
+}
+// write the ghosted state U as dump number `step` exactly as SolverBase::save_solution would (piece + .pvti when decomposed)
+int ekh_case_save_vti(void* h, const double* U, int step, char* path_out, int cap)
+{
+  if (!h || !U) return 1;
+  HostCase* c = static_cast<HostCase*>(h);
+  const HydroParams& p = *c->params;
+  std::map<int, std::string> names;
+  const char* hydro2[] = { "rho", "energy", "rho_vx", "rho_vy" };
+  const char* all8[] = { "rho", "energy", "rho_vx", "rho_vy", "rho_vz", "bx", "by", "bz" };
+  for (int v = 0; v < p.nbvar; ++v)
+    names[v] = (p.nbvar == 4) ? hydro2[v] : all8[v]; // SolverBase.cpp:60-67
+  const std::string f = save_vti(U, p, c->configMap, p.nbvar, names, step);
+  if (f.empty()) return 2;
+  if (path_out && cap > 0) {
+    strncpy(path_out, f.c_str(), (size_t)cap - 1);
+    path_out[cap - 1] = 0;
+  }
   return 0;
 }
 int ekh_solver_registered(const char* name) { return SolverFactory::Instance().has(name) ? 1 : 0; }

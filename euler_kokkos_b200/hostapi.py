@@ -29,6 +29,7 @@ hlib.ekh_case_get_float.restype = C.c_double
 hlib.ekh_case_get_float.argtypes = [_vp, C.c_char_p, C.c_char_p, C.c_float]
 hlib.ekh_case_init_state.argtypes = [_vp, _vp, _vp]
 hlib.ekh_case_write_ini.argtypes = [_vp, C.c_char_p]
+hlib.ekh_case_save_vti.argtypes = [_vp, _vp, C.c_int, C.c_char_p, C.c_int]
 hlib.ekh_solver_registered.argtypes = [C.c_char_p]
 hlib.ekh_run_ini.argtypes = [C.c_char_p, C.c_char_p]
 
@@ -110,6 +111,16 @@ class Case:
         grav = np.zeros((self.params.dim,) + tuple(self.params.shape[1:])) if self.params.gravity_enabled else None
         self.init_state(U, grav)
         return U, grav
+
+    def save_vti(self, U: np.ndarray, step: int) -> str:
+        """Write dump `step` as the C++ driver does: <prefix>_%07d.vti, or for a decomposed case this rank's piece
+        <prefix>_time%07d_mpi%05d.vti (+ the .pvti header from rank 0).  Returns the file written."""
+        assert U.dtype == np.float64 and U.flags["C_CONTIGUOUS"] and U.shape == tuple(self.params.shape)
+        buf = C.create_string_buffer(1024)
+        rc = hlib.ekh_case_save_vti(self._h, U.ctypes.data_as(_vp), int(step), buf, 1024)
+        if rc != 0:
+            raise OSError(f"cannot write the .vti dump (rc={rc})")
+        return buf.value.decode()
 
     def write_ini(self, path: str):
         rc = hlib.ekh_case_write_ini(self._h, path.encode())

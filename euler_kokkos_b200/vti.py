@@ -44,6 +44,29 @@ def read_vti(path: str):
     return names, np.stack(out).astype(np.float64)
 
 
+def read_pvti(path: str):
+    """Assemble a decomposed dump: parse the .pvti header (write_pvti_header, IO_VTK.cpp:857-1011), read every piece
+    and place it by its extent.  Returns (names, data) with data shaped (nvar, NZ, NY, NX) for the global box."""
+    import os
+
+    with open(path) as f:
+        text = f.read()
+    m = re.search(r'<PImageData WholeExtent="\s*(\d+)\s+(\d+)\s+(\d+)\s+(\d+)\s+(\d+)\s+(\d+)', text)
+    if not m:
+        raise ValueError(f"{path}: no PImageData WholeExtent")
+    e = [int(x) for x in m.groups()]
+    NX, NY, NZ = e[1] - e[0], e[3] - e[2], max(e[5] - e[4], 1)
+    names = re.findall(r'<PDataArray type="Float64" Name="(\w+)"', text)
+    out = np.full((len(names), NZ, NY, NX), np.nan)
+    for pm in re.finditer(r'<Piece Extent="([^"]+)" Source="([^"]+)"', text):
+        ext = [int(x) for x in pm.group(1).split()]
+        pnames, data = read_vti(os.path.join(os.path.dirname(path), pm.group(2)))
+        assert pnames == names, (pnames, names)
+        z0 = ext[4] if NZ > 1 else 0
+        out[:, z0:z0 + data.shape[1], ext[2]:ext[2] + data.shape[2], ext[0]:ext[0] + data.shape[3]] = data
+    return names, out
+
+
 def embed_interior(interior: np.ndarray, ghost: int, dim: int) -> np.ndarray:
     """(nvar,nz,ny,nx) interior -> ghosted SoA (nvar,ksize,jsize,isize); ghosts are zero-filled."""
     nv, nz, ny, nx = interior.shape

@@ -144,3 +144,39 @@ def test_slab_decomposition_neighbours_and_copy_faces():
     c0 = hostapi.Case(ini, {"mesh.nz": 8}, rank=0, nranks=2)
     c1 = hostapi.Case(ini, {"mesh.nz": 8}, rank=1, nranks=2)
     assert list(c0.params.bc)[4:] == [1, 4] and list(c1.params.bc)[4:] == [4, 1]
+
+
+@pytest.mark.parametrize("ini,ov,world", [("test_implode_3D.ini", {"mesh.nx": 12, "mesh.ny": 10, "mesh.nz": 6}, 3),
+                                          ("test_implode_3D_mpi.ini", {"mesh.nx": 6, "mesh.ny": 5, "mesh.nz": 4}, 16),
+                                          ("test_implode_2D.ini", {"mesh.nx": 16, "mesh.ny": 6}, 2)])
+def test_decomposed_dump_is_a_pvti_collection_of_the_single_domain_dump(tmp_path, ini, ov, world):
+    """Decomposed runs write the reference's parallel VTK layout (save_VTK_*_mpi + write_pvti_header, IO_VTK.cpp:415-1011):
+    <prefix>_time%07d_mpi%05d.vti pieces with global extents + a .pvti header; reassembled, they are the dump of the
+    same global grid on one rank."""
+    from euler_kokkos_b200 import hostapi
+    from euler_kokkos_b200.vti import interior_of, read_pvti, read_vti
+
+    path = hostapi.settings(ini)
+    ov = dict(ov)
+    ov.update({"output.outputdir": str(tmp_path), "output.outputprefix": "d"})
+    cases = [hostapi.Case(path, ov, rank=r, nranks=world) for r in range(world)]
+    dims = cases[0].mpi_dims
+    for c in cases:
+        U, _ = c.new_state()
+        f = c.save_vti(U, 3)
+        assert f.endswith("_time0000003_mpi%05d.vti" % cases.index(c))
+    names, got = read_pvti(str(tmp_path / "d_time0000003.pvti"))
+    # the same global grid on one rank
+    p0 = cases[0].params
+    ov1 = dict(ov)
+    ov1.update({"mesh.nx": p0.nx * dims[0], "mesh.ny": p0.ny * dims[1], "mpi.mx": 1, "mpi.my": 1, "mpi.mz": 1, "output.outputprefix": "s"})
+    if p0.dim == 3:
+        ov1["mesh.nz"] = p0.nz * dims[2]
+    one = hostapi.Case(path, ov1)
+    U1, _ = one.new_state()
+    f1 = one.save_vti(U1, 3)
+    assert f1.endswith("s_0000003.vti")
+    names1, ref = read_vti(f1)
+    assert names == names1 and got.shape == ref.shape
+    assert np.array_equal(got, ref)
+    assert np.array_equal(ref, interior_of(U1, p0.ghost, p0.dim))
