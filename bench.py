@@ -364,7 +364,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="blast3d", choices=sorted(WORKLOADS))
-    ap.add_argument("--n", type=int, default=None, help="cubic interior size per GPU (default 512)")
+    ap.add_argument("--n", "--size", dest="n", type=int, default=None, help="cubic interior size per GPU (default 512); use --size under torchrun, whose own parser claims --n")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -251,7 +251,20 @@ static int enqueue_step(Ctx& c, int use_host_dt, double host_dt, int max_steps)
     pre_step_kernel<<<1, 1, 0, c.stream>>>(c.ts, c.p.cfl, use_host_dt, host_dt);
     c.launches++;
     ktime_mark(c);
-    EK_CUDA(&c, launch_mhd_step(c, Uin, Uout));
+    if (c.overlap_ok) {
+      // every stage, the update of the END planes first; they travel to the z neighbours beside the update of the rest
+      EK_CUDA(&c, launch_mhd_step(c, Uin, Uout, 1));
+      EK_CUDA(&c, cudaEventRecord(c.ev_edge, c.stream));
+      EK_CUDA(&c, cudaStreamWaitEvent(c.comm_stream, c.ev_edge, 0));
+      rc = comm_exchange_dir(c, Uout, 2, c.comm_stream);
+      if (rc != EK_OK)
+        return rc;
+      EK_CUDA(&c, cudaEventRecord(c.ev_halo, c.comm_stream));
+      c.halo_ready_for = Uout;
+      EK_CUDA(&c, launch_mhd_step(c, Uin, Uout, 2));
+    } else {
+      EK_CUDA(&c, launch_mhd_step(c, Uin, Uout));
+    }
     ktime_mark(c);
   } else {
     // hydro: dt (from the previous update's fused reduction) -> boundaries -> fused step

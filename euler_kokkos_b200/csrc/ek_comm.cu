@@ -230,14 +230,15 @@ int ek_comm_attach(ek_ctx* ctx, const void* id, int rank, int nranks, const int3
   }
   c->dt_primed = false;
   c->halo_ready_for = nullptr;
-  // Overlap of the z-halo exchange with the interior of the step: hydro 3-D, slabs along z only, and a z extent
-  // that can be cut into end + middle chunks.  Every rank must take the same decision (it changes the order of
+  // Overlap of the z-halo exchange with the interior of the step: 3-D, slabs along z only, and a z extent that can
+  // be cut into end + middle parts (hydro: z-chunks of the fused kernel; MHD: planes of the update stage).  Every rank must take the same decision (it changes the order of
   // the NCCL calls), hence the min-reduction.
   {
     const bool want = !(getenv("EK_HALO_OVERLAP") && atoi(getenv("EK_HALO_OVERLAP")) == 0);
     const bool zcopy = c->p.bc[4] == EK_BC_COPY || c->p.bc[5] == EK_BC_COPY;
     const bool xycopy = c->p.bc[0] == EK_BC_COPY || c->p.bc[1] == EK_BC_COPY || c->p.bc[2] == EK_BC_COPY || c->p.bc[3] == EK_BC_COPY;
-    double ok = (want && !c->p.mhd && c->p.dim == 3 && zcopy && !xycopy && hydro_z_splittable(*c)) ? 1.0 : 0.0;
+    const bool splittable = c->p.mhd ? (c->p.nz >= 2 * c->p.ghost) : hydro_z_splittable(*c);
+    double ok = (want && c->p.dim == 3 && zcopy && !xycopy && splittable) ? 1.0 : 0.0;
     if (nranks > 1) {
       if (cudaMemcpyAsync(c->scratch, &ok, sizeof(double), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { c->err = "overlap probe: H2D failed"; return EK_ERR_CUDA; }
       EK_NCCL(*c, api->AllReduce(c->scratch, c->scratch, 1, ncclDouble, ncclMin, comm, c->stream));

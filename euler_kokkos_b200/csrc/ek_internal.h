@@ -66,7 +66,7 @@ cudaError_t launch_hydro_step(Ctx& c, const double* Uin, double* Uout, int part 
 bool hydro_z_splittable(const Ctx& c);
 cudaError_t launch_hydro_invdt(Ctx& c, const double* U);
 // mhd_launch.cu
-cudaError_t launch_mhd_step(Ctx& c, const double* Uin, double* Uout);
+cudaError_t launch_mhd_step(Ctx& c, const double* Uin, double* Uout, int part = 0);
 cudaError_t launch_mhd_invdt(Ctx& c, const double* U);
 size_t mhd_work_bytes(const Grid& g);
 // ek_comm.cu

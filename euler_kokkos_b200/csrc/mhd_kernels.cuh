@@ -17,11 +17,13 @@ struct MhdArgs {
   double* __restrict__ work;
   TimeState* ts;
   MhdChunkMap cm; // thread -> cell order of the 3-D stencil stages (yc = 0: flat)
+  unsigned t0 = 0; // offset added to the linear thread index (flat order: launches restricted to a range of planes)
+  int upd_klo = 0, upd_khi = 1 << 30; // planes [upd_klo, upd_khi) the update kernel may write
 };
 
 __device__ __forceinline__ bool mhd_cell_of_thread(const MhdArgs& a, MhdIdx& x)
 {
-  return mhd_chunk_cell(a.g, a.cm, blockIdx.x * blockDim.x + threadIdx.x, x);
+  return mhd_chunk_cell(a.g, a.cm, a.t0 + blockIdx.x * blockDim.x + threadIdx.x, x);
 }
 
 __device__ __forceinline__ bool mhd_cell_of_thread(const Grid& g, MhdIdx& x)
@@ -151,7 +153,7 @@ __global__ void __launch_bounds__(256) mhd_update_kernel(const MhdArgs a)
   const MhdWork w = mhd_work_split(a.work, a.g.sv);
   const double dt = a.ts->dt;
   MhdIdx x;
-  if (mhd_cell_of_thread(a, x))
+  if (mhd_cell_of_thread(a, x) && x.k >= a.upd_klo && x.k < a.upd_khi)
     mhd_stage_update(a.g, a.Uin, w.F, w.EMF, a.Uout, dt / a.g.dx, dt / a.g.dy, dt / a.g.dz, x);
 }
 

@@ -52,10 +52,37 @@ cudaError_t launch_mhd_invdt(Ctx& c, const double* U)
   return cudaGetLastError();
 }
 
+// stage U restricted to planes: the END planes (first and last gw interior planes, what the z neighbours need as
+// ghosts) as two small flat launches, or the MIDDLE planes with the regular launch order
+static void launch_update_ends(Ctx& c, MhdArgs a)
+{
+  const Grid& g = c.g;
+  a.cm = mhd_chunk_map(g, 0, 1); // flat: thread = cell
+  const unsigned per_plane = (unsigned)g.sk;
+  const int k0[2] = { g.gw, g.nz };
+  for (int e = 0; e < 2; ++e) {
+    a.t0 = per_plane * (unsigned)k0[e];
+    a.upd_klo = k0[e];
+    a.upd_khi = k0[e] + g.gw;
+    const unsigned nthreads = per_plane * (unsigned)g.gw;
+    mhd_update_kernel<<<(nthreads + 255) / 256, 256, 0, c.stream>>>(a);
+    c.launches++;
+  }
+}
+
+// part: 0 = the whole step; 1 = every stage, but the update only on the END planes; 2 = the update of the MIDDLE planes
 template <int RS>
-static cudaError_t launch_step(Ctx& c, const double* Uin, double* Uout)
+static cudaError_t launch_step(Ctx& c, const double* Uin, double* Uout, int part)
 {
   const MhdArgs a = make_args(c, Uin, Uout);
+  if (part == 2) {
+    MhdArgs m = zgrouped(c, a, 256);
+    m.upd_klo = 2 * c.g.gw;
+    m.upd_khi = c.g.nz;
+    mhd_update_kernel<<<blocks(m, 256), 256, 0, c.stream>>>(m);
+    c.launches++;
+    return cudaGetLastError();
+  }
   if (c.mhd_prims_of != Uin) { // dt given by the host: the primitives have not been computed yet
     mhd_prims_kernel<<<blocks(c.g, 256), 256, 0, c.stream>>>(a, 0);
     c.launches++;
@@ -89,7 +116,10 @@ static cudaError_t launch_step(Ctx& c, const double* Uin, double* Uout)
     mhd_emf_kernel<<<blocks(a4, 128), 128, 0, c.stream>>>(a4);
     c.launches += 5;
   }
-  mhd_update_kernel<<<blocks(a8, 256), 256, 0, c.stream>>>(a8);
+  if (part == 1)
+    launch_update_ends(c, a);
+  else
+    mhd_update_kernel<<<blocks(a8, 256), 256, 0, c.stream>>>(a8);
   return cudaGetLastError();
 }
 
@@ -110,7 +140,7 @@ static cudaError_t launch_step_2d(Ctx& c, const double* Uin, double* Uout)
   return cudaGetLastError();
 }
 
-cudaError_t launch_mhd_step(Ctx& c, const double* Uin, double* Uout)
+cudaError_t launch_mhd_step(Ctx& c, const double* Uin, double* Uout, int part)
 {
   if (c.p.dim == 2) {
     switch (c.p.riemann) {
@@ -121,9 +151,9 @@ cudaError_t launch_mhd_step(Ctx& c, const double* Uin, double* Uout)
     }
   }
   switch (c.p.riemann) {
-    case RIEMANN_HLLD: return launch_step<RIEMANN_HLLD>(c, Uin, Uout);
-    case RIEMANN_HLL: return launch_step<RIEMANN_HLL>(c, Uin, Uout);
-    case RIEMANN_LLF: return launch_step<RIEMANN_LLF>(c, Uin, Uout);
+    case RIEMANN_HLLD: return launch_step<RIEMANN_HLLD>(c, Uin, Uout, part);
+    case RIEMANN_HLL: return launch_step<RIEMANN_HLL>(c, Uin, Uout, part);
+    case RIEMANN_LLF: return launch_step<RIEMANN_LLF>(c, Uin, Uout, part);
     default: return cudaErrorInvalidValue;
   }
 }

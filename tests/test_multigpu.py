@@ -88,5 +88,8 @@ def test_hydro3d_two_slabs_periodic_z_with_gravity(tmp_path):
               16, 2, 6, tmp_path, 1e-13)
 
 
-def test_mhd3d_two_slabs_periodic_match_single_domain(tmp_path):
+@pytest.mark.parametrize("overlap", ["1", "0"])
+def test_mhd3d_two_slabs_periodic_match_single_domain(tmp_path, monkeypatch, overlap):
+    """overlap=1: the update stage does the END planes first and their exchange runs beside the update of the rest"""
+    monkeypatch.setenv("EK_HALO_OVERLAP", overlap)
     _run_case("test_mhd_orszag_tang_3D.ini", {"mesh.nx": 32, "mesh.ny": 32}, 12, 2, 8, tmp_path, 1e-13)
