@@ -166,17 +166,24 @@ EK_HD bool mhd_chunk_cell(const Grid& g, const MhdChunkMap& m, unsigned t, MhdId
 // ---- stage P ------------------------------------------------------------------------------------
 // Q(i,j,k) for 0 <= i < isize-1 (the last layer is never written, MHDRunFunctors3D.h:120-122);
 // returns the cell's inverse-dt contribution (0 outside the interior).
-EK_HD double mhd_stage_prims(const Grid& g, const double* __restrict__ U, double* __restrict__ Q, const MhdIdx& x)
+// primitives of one cell (0 <= i < isize-1 etc., checked by the caller) into q[8]
+EK_HD void mhd_prims_at(const Grid& g, const double* __restrict__ U, const MhdIdx& x, double* __restrict__ q)
 {
-  if (x.i >= g.isize - 1 || x.j >= g.jsize - 1 || x.k >= g.ksize - 1)
-    return 0.0;
   const double* __restrict__ Uc = U + x.c;
   const long long sv = g.sv;
-  double u[8], q[8];
+  double u[8];
 #pragma unroll
   for (int v = 0; v < 8; ++v)
     u[v] = Uc[sv * v];
   mhd_cons_to_prim(g, u, Uc[sv * IA + 1], Uc[sv * IB + x.sj], Uc[sv * IC + x.sk], q);
+}
+
+EK_HD double mhd_stage_prims(const Grid& g, const double* __restrict__ U, double* __restrict__ Q, const MhdIdx& x)
+{
+  if (x.i >= g.isize - 1 || x.j >= g.jsize - 1 || x.k >= g.ksize - 1)
+    return 0.0;
+  double q[8];
+  mhd_prims_at(g, U, x, q);
   double* __restrict__ Qc = Q + tile_off<8>(x.c);
 #pragma unroll
   for (int v = 0; v < 8; ++v)
@@ -189,21 +196,23 @@ EK_HD double mhd_stage_prims(const Grid& g, const double* __restrict__ U, double
 
 // ---- stage E ------------------------------------------------------------------------------------
 // E at the three lower edges of cell (i,j,k), 1 <= i <= isize-2 (MHDRunFunctors3D.h:303-352)
-EK_HD void mhd_stage_elec(const Grid& g, const double* __restrict__ U, const double* __restrict__ Q, double* __restrict__ E,
-                          const MhdIdx& x)
+// Tile pointers (variable v at p[TL*v]) of the primitives of the 7 cells touching the three lower edges of a cell:
+// qXYZ = cell shifted by -X, -Y, -Z.  They may point into the global Q array or into a staged copy in shared memory.
+struct MhdElecQ {
+  const double *q000, *q100, *q010, *q001, *q110, *q101, *q011;
+};
+
+EK_HD bool mhd_elec_active(const Grid& g, const MhdIdx& x)
 {
-  if (x.i < 1 || x.j < 1 || x.k < 1 || x.i > g.isize - 2 || x.j > g.jsize - 2 || x.k > g.ksize - 2)
-    return;
+  return !(x.i < 1 || x.j < 1 || x.k < 1 || x.i > g.isize - 2 || x.j > g.jsize - 2 || x.k > g.ksize - 2);
+}
+
+// Ec: tile pointer of the output (Ex, Ey, Ez at Ec[0], Ec[TL], Ec[2*TL])
+EK_HD void mhd_elec_core(const Grid& g, const double* __restrict__ U, const MhdIdx& x, const MhdElecQ& P, double* __restrict__ Ec)
+{
   const unsigned c = x.c, sj = x.sj, sk = x.sk;
   const long long sv = g.sv;
-  // velocities of the 7 cells touching the three lower edges
-  const double* __restrict__ q000 = Q + tile_off<8>(c);
-  const double* __restrict__ q100 = Q + tile_off<8>(c - 1);
-  const double* __restrict__ q010 = Q + tile_off<8>(c - sj);
-  const double* __restrict__ q001 = Q + tile_off<8>(c - sk);
-  const double* __restrict__ q110 = Q + tile_off<8>(c - 1 - sj);
-  const double* __restrict__ q101 = Q + tile_off<8>(c - 1 - sk);
-  const double* __restrict__ q011 = Q + tile_off<8>(c - sj - sk);
+  const double *q000 = P.q000, *q100 = P.q100, *q010 = P.q010, *q001 = P.q001, *q110 = P.q110, *q101 = P.q101, *q011 = P.q011;
   const double* __restrict__ UA = U + sv * IA + c;
   const double* __restrict__ UB = U + sv * IB + c;
   const double* __restrict__ UC = U + sv * IC + c;
@@ -213,7 +222,6 @@ EK_HD void mhd_stage_elec(const Grid& g, const double* __restrict__ U, const dou
   w = 0.25 * (q011[TL * IW] + q010[TL * IW] + q001[TL * IW] + q000[TL * IW]);
   B = 0.5 * (UB[-(long long)sk] + B0);
   C = 0.5 * (UC[-(long long)sj] + C0);
-  double* __restrict__ Ec = E + tile_off<3>(c);
   Ec[0] = v * C - w * B;
   u = 0.25 * (q101[TL * IU] + q100[TL * IU] + q001[TL * IU] + q000[TL * IU]);
   w = 0.25 * (q101[TL * IW] + q100[TL * IW] + q001[TL * IW] + q000[TL * IW]);
@@ -227,29 +235,56 @@ EK_HD void mhd_stage_elec(const Grid& g, const double* __restrict__ U, const dou
   Ec[2 * TL] = u * B - v * A;
 }
 
+EK_HD void mhd_stage_elec(const Grid& g, const double* __restrict__ U, const double* __restrict__ Q, double* __restrict__ E,
+                          const MhdIdx& x)
+{
+  if (!mhd_elec_active(g, x))
+    return;
+  const unsigned c = x.c, sj = x.sj, sk = x.sk;
+  MhdElecQ P;
+  P.q000 = Q + tile_off<8>(c);
+  P.q100 = Q + tile_off<8>(c - 1);
+  P.q010 = Q + tile_off<8>(c - sj);
+  P.q001 = Q + tile_off<8>(c - sk);
+  P.q110 = Q + tile_off<8>(c - 1 - sj);
+  P.q101 = Q + tile_off<8>(c - 1 - sk);
+  P.q011 = Q + tile_off<8>(c - sj - sk);
+  mhd_elec_core(g, U, x, P, E + tile_off<3>(c));
+}
+
 // ---- stage T ------------------------------------------------------------------------------------
 // Hancock predictor of cell (i,j,k) (trace_unsplit_mhd_3d_simpler, MHDBaseFunctor3D.h:690-914) and of
 // its three lower faces.  Cells in [2, isize-3], faces in [2, isize-2] (what stage R consumes).
-EK_HD void mhd_stage_trace(const Grid& g, const double* __restrict__ U, const double* __restrict__ Q, const double* __restrict__ E,
-                           double* __restrict__ S, double dtdx, double dtdy, double dtdz, const MhdIdx& x)
+// Tile pointers of what the Hancock predictor of one cell reads from the work arrays: primitives of the cell and of
+// its six neighbours, edge fields of the cell and of its +x, +y, +z neighbours (global arrays or staged copies).
+struct MhdTraceIn {
+  const double *Q0, *Qxm, *Qxp, *Qym, *Qyp, *Qzm, *Qzp;
+  const double *E0, *Ei, *Ej, *Ek;
+};
+
+EK_HD bool mhd_trace_active(const Grid& g, const MhdIdx& x)
 {
-  if (x.i < 2 || x.j < 2 || x.k < 2 || x.i > g.isize - 2 || x.j > g.jsize - 2 || x.k > g.ksize - 2)
-    return;
+  return !(x.i < 2 || x.j < 2 || x.k < 2 || x.i > g.isize - 2 || x.j > g.jsize - 2 || x.k > g.ksize - 2);
+}
+
+// Sc: tile pointer of the cell's compact state (output)
+EK_HD void mhd_trace_core(const Grid& g, const double* __restrict__ U, const MhdTraceIn& P, double* __restrict__ Sc, double dtdx,
+                          double dtdy, double dtdz, const MhdIdx& x)
+{
   const unsigned c = x.c;
   const long long sj = x.sj, sk = x.sk, sv = g.sv;
   const double* __restrict__ UA = U + sv * IA + c;
   const double* __restrict__ UB = U + sv * IB + c;
   const double* __restrict__ UC = U + sv * IC + c;
-  const double* __restrict__ E0 = E + tile_off<3>(c);
+  const double* __restrict__ E0 = P.E0;
   const bool in_i = x.i <= g.isize - 3, in_j = x.j <= g.jsize - 3, in_k = x.k <= g.ksize - 3;
   const double xst = dmin(g.slope_type, 2.0); // slope_unsplit_mhd_3d, MHDBaseFunctor3D.h:600
-  double* __restrict__ Sc = S + tile_off<S_TOTAL>(c);
 
   const double AL = UA[0], BL = UB[0], CL = UC[0];
   const double ELL = E0[0], FLL = E0[TL], GLL = E0[2 * TL];
-  const double* __restrict__ Ei = E + tile_off<3>(c + 1);
-  const double* __restrict__ Ej = E + tile_off<3>(c + x.sj);
-  const double* __restrict__ Ek = E + tile_off<3>(c + x.sk);
+  const double* __restrict__ Ei = P.Ei;
+  const double* __restrict__ Ej = P.Ej;
+  const double* __restrict__ Ek = P.Ek;
   // face-centred half step: AL + sAL0 etc. (:872-877, :889-894) and halved transverse slopes (:810-822)
   if (in_j && in_k) {
     const double GLR = Ej[2 * TL], FLR = Ek[TL];
@@ -277,7 +312,7 @@ EK_HD void mhd_stage_trace(const Grid& g, const double* __restrict__ U, const do
   const double st = g.slope_type;
   const double sth = 0.5 * st;
   const bool use_slopes = (st == 1.0 || st == 2.0); // slope_unsplit_hydro_3d, :379,:470
-  const double* __restrict__ Q0 = Q + tile_off<8>(c);
+  const double* __restrict__ Q0 = P.Q0;
   double q[8];
 #pragma unroll
   for (int v = 0; v < 8; ++v)
@@ -287,8 +322,8 @@ EK_HD void mhd_stage_trace(const Grid& g, const double* __restrict__ U, const do
   const double gp = g.gamma0 * p;
   double sr0, sp0, su0, sv0, sw0, sA0, sB0, sC0;
   {
-    const double* __restrict__ Qm = Q + tile_off<8>(c - 1);
-    const double* __restrict__ Qp = Q + tile_off<8>(c + 1);
+    const double* __restrict__ Qm = P.Qxm;
+    const double* __restrict__ Qp = P.Qxp;
     double d[8];
 #pragma unroll
     for (int n = 0; n < 8; ++n)
@@ -306,8 +341,8 @@ EK_HD void mhd_stage_trace(const Grid& g, const double* __restrict__ U, const do
     Sc[TL * (SX + 5)] = dBx; Sc[TL * (SX + 6)] = dCx;
   }
   {
-    const double* __restrict__ Qm = Q + tile_off<8>(c - x.sj);
-    const double* __restrict__ Qp = Q + tile_off<8>(c + x.sj);
+    const double* __restrict__ Qm = P.Qym;
+    const double* __restrict__ Qp = P.Qyp;
     double d[8];
 #pragma unroll
     for (int n = 0; n < 8; ++n)
@@ -325,8 +360,8 @@ EK_HD void mhd_stage_trace(const Grid& g, const double* __restrict__ U, const do
     Sc[TL * (SY + 5)] = dAy; Sc[TL * (SY + 6)] = dCy;
   }
   {
-    const double* __restrict__ Qm = Q + tile_off<8>(c - x.sk);
-    const double* __restrict__ Qp = Q + tile_off<8>(c + x.sk);
+    const double* __restrict__ Qm = P.Qzm;
+    const double* __restrict__ Qp = P.Qzp;
     double d[8];
 #pragma unroll
     for (int n = 0; n < 8; ++n)
@@ -351,6 +386,27 @@ EK_HD void mhd_stage_trace(const Grid& g, const double* __restrict__ U, const do
   Sc[TL * (SC + IA)] = A + sA0;
   Sc[TL * (SC + IB)] = B + sB0;
   Sc[TL * (SC + IC)] = C + sC0;
+}
+
+EK_HD void mhd_stage_trace(const Grid& g, const double* __restrict__ U, const double* __restrict__ Q, const double* __restrict__ E,
+                           double* __restrict__ S, double dtdx, double dtdy, double dtdz, const MhdIdx& x)
+{
+  if (!mhd_trace_active(g, x))
+    return;
+  const unsigned c = x.c;
+  MhdTraceIn P;
+  P.Q0 = Q + tile_off<8>(c);
+  P.Qxm = Q + tile_off<8>(c - 1);
+  P.Qxp = Q + tile_off<8>(c + 1);
+  P.Qym = Q + tile_off<8>(c - x.sj);
+  P.Qyp = Q + tile_off<8>(c + x.sj);
+  P.Qzm = Q + tile_off<8>(c - x.sk);
+  P.Qzp = Q + tile_off<8>(c + x.sk);
+  P.E0 = E + tile_off<3>(c);
+  P.Ei = E + tile_off<3>(c + 1);
+  P.Ej = E + tile_off<3>(c + x.sj);
+  P.Ek = E + tile_off<3>(c + x.sk);
+  mhd_trace_core(g, U, P, S + tile_off<S_TOTAL>(c), dtdx, dtdy, dtdz, x);
 }
 
 // ---- stage R ------------------------------------------------------------------------------------

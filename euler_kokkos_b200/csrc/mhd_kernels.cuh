@@ -45,15 +45,26 @@ __device__ __forceinline__ bool mhd_cell_of_thread(const Grid& g, MhdIdx& x)
 }
 
 // stage P + CFL max-reduction (warp shuffles, then one atomic per CTA: grid reduce)
-__global__ void __launch_bounds__(256) mhd_prims_kernel(const MhdArgs a, const int do_invdt)
+// store_q = 0: CFL reduction only (the fused P+E+T kernel recomputes the primitives it needs)
+__global__ void __launch_bounds__(256) mhd_prims_kernel(const MhdArgs a, const int do_invdt, const int store_q = 1)
 {
   if (a.ts->finished)
     return;
   const MhdWork w = mhd_work_split(a.work, a.g.sv);
   MhdIdx x;
   double m = 0.0;
-  if (mhd_cell_of_thread(a.g, x))
-    m = mhd_stage_prims(a.g, a.Uin, w.Q, x);
+  if (mhd_cell_of_thread(a.g, x)) {
+    if (store_q) {
+      m = mhd_stage_prims(a.g, a.Uin, w.Q, x);
+    } else {
+      const int gw = a.g.gw;
+      if (x.i >= gw && x.i < a.g.isize - gw && x.j >= gw && x.j < a.g.jsize - gw && x.k >= gw && x.k < a.g.ksize - gw) {
+        double q[8];
+        mhd_prims_at(a.g, a.Uin, x, q);
+        m = mhd_cell_invdt(a.g, q);
+      }
+    }
+  }
   if (!do_invdt)
     return;
   __shared__ double red[8];
@@ -244,3 +255,4 @@ __global__ void __launch_bounds__(256) mhd2d_update_kernel(const MhdArgs a)
 } // namespace ek
 
 #include "mhd_staged.cuh"
+#include "mhd_pet.cuh"

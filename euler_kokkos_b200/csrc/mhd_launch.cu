@@ -33,6 +33,13 @@ static MhdArgs zgrouped(const Ctx& c, MhdArgs a, int threads)
   return a;
 }
 
+// fused P+E+T kernel (mhd_pet.cuh); EK_MHD_PET=0 selects the three staged kernels
+static bool use_pet(const Ctx& c)
+{
+  const int pet = getenv("EK_MHD_PET") ? atoi(getenv("EK_MHD_PET")) : 1;
+  return pet != 0 && c.p.dim == 3;
+}
+
 static unsigned blocks(const Grid& g, int threads) { return (unsigned)((g.sv + threads - 1) / threads); }
 static unsigned blocks(const MhdArgs& a, int threads)
 {
@@ -46,7 +53,7 @@ cudaError_t launch_mhd_invdt(Ctx& c, const double* U)
   if (c.p.dim == 2)
     mhd2d_prims_kernel<<<blocks(c.g, 256), 256, 0, c.stream>>>(a, 1);
   else
-    mhd_prims_kernel<<<blocks(c.g, 256), 256, 0, c.stream>>>(a, 1);
+    mhd_prims_kernel<<<blocks(c.g, 256), 256, 0, c.stream>>>(a, 1, use_pet(c) ? 0 : 1);
   c.launches++;
   c.mhd_prims_of = U;
   return cudaGetLastError();
@@ -83,21 +90,55 @@ static cudaError_t launch_step(Ctx& c, const double* Uin, double* Uout, int part
     c.launches++;
     return cudaGetLastError();
   }
-  if (c.mhd_prims_of != Uin) { // dt given by the host: the primitives have not been computed yet
-    mhd_prims_kernel<<<blocks(c.g, 256), 256, 0, c.stream>>>(a, 0);
-    c.launches++;
-  }
-  c.mhd_prims_of = nullptr;
   const MhdArgs a8 = zgrouped(c, a, 256), a4 = zgrouped(c, a, 128);
-  mhd_elec_kernel<<<blocks(a8, 256), 256, 0, c.stream>>>(a8);
-  mhd_trace_kernel<<<blocks(a8, 256), 256, 0, c.stream>>>(a8);
+  if (use_pet(c)) {
+    static bool pet_attr[16] = { false };
+    if (!pet_attr[c.device & 15]) {
+      cudaError_t e = cudaFuncSetAttribute(mhd_pet_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PetSmem));
+      if (e != cudaSuccess)
+        return e;
+      pet_attr[c.device & 15] = true;
+    }
+    const Grid& g = c.g;
+    dim3 grid((g.isize - 3 + PET_TX - 1) / PET_TX, (g.jsize - 3 + PET_TY - 1) / PET_TY, 1); // cells 2 .. isize-2
+    const int nplanes = g.ksize - 3;                                                          // planes 2 .. ksize-2
+    // enough CTAs for whole waves (2 resident CTAs per SM), chunks long enough to amortise the 3-plane warm-up
+    const long long slots = 2LL * c.sm_count, xy = (long long)grid.x * grid.y;
+    int nchunk = 1;
+    double best = 1e300;
+    for (int n = 1; n <= nplanes; ++n) {
+      const int zc = (nplanes + n - 1) / n;
+      if (zc < 16 && n > 1)
+        break;
+      const long long ctas = xy * ((nplanes + zc - 1) / zc);
+      const double cost = (double)(((ctas + slots - 1) / slots) * slots) / (double)ctas * (zc + 3.0) / zc;
+      if (cost < best - 1e-12) {
+        best = cost;
+        nchunk = n;
+      }
+    }
+    const int zchunk = (nplanes + nchunk - 1) / nchunk;
+    grid.z = (nplanes + zchunk - 1) / zchunk;
+    mhd_pet_kernel<0><<<grid, PET_TX * PET_TY, sizeof(PetSmem), c.stream>>>(a, zchunk);
+    c.launches++;
+    c.mhd_prims_of = nullptr;
+  } else {
+    if (c.mhd_prims_of != Uin) { // dt given by the host: the primitives have not been computed yet
+      mhd_prims_kernel<<<blocks(c.g, 256), 256, 0, c.stream>>>(a, 0);
+      c.launches++;
+    }
+    c.mhd_prims_of = nullptr;
+    mhd_elec_kernel<<<blocks(a8, 256), 256, 0, c.stream>>>(a8);
+    mhd_trace_kernel<<<blocks(a8, 256), 256, 0, c.stream>>>(a8);
+    c.launches += 2;
+  }
   const int fuse_r = getenv("EK_MHD_FUSE_R") ? atoi(getenv("EK_MHD_FUSE_R")) : 1; // tuning switch (default: fused)
   // stage R variant: 2 (default) = plain loads + Riemann solvers as real functions; 1 = cp.async software pipeline;
   // 0 = fully inlined (mhd_staged.cuh has the measurements)
   const int staged = getenv("EK_MHD_STAGED") ? atoi(getenv("EK_MHD_STAGED")) : 2;
   if (staged == 2) {
     mhd_faces_edges_call_kernel<RS><<<blocks(a4, 128), 128, 0, c.stream>>>(a4);
-    c.launches += 4;
+    c.launches++;
   } else if (staged) {
     static bool attr_done[16] = { false };
     if (!attr_done[c.device & 15]) {
@@ -107,19 +148,21 @@ static cudaError_t launch_step(Ctx& c, const double* Uin, double* Uout, int part
       attr_done[c.device & 15] = true;
     }
     mhd_faces_edges_staged_kernel<RS><<<blocks(a4, STG_THREADS), STG_THREADS, STG_SMEM_BYTES, c.stream>>>(a4);
-    c.launches += 4;
+    c.launches++;
   } else if (fuse_r) {
     mhd_faces_edges_kernel<RS><<<blocks(a4, 128), 128, 0, c.stream>>>(a4);
-    c.launches += 4;
+    c.launches++;
   } else {
     mhd_flux_kernel<RS><<<blocks(a4, 128), 128, 0, c.stream>>>(a4);
     mhd_emf_kernel<<<blocks(a4, 128), 128, 0, c.stream>>>(a4);
-    c.launches += 5;
+    c.launches += 2;
   }
-  if (part == 1)
+  if (part == 1) {
     launch_update_ends(c, a);
-  else
+  } else {
     mhd_update_kernel<<<blocks(a8, 256), 256, 0, c.stream>>>(a8);
+    c.launches++;
+  }
   return cudaGetLastError();
 }
 
