@@ -123,6 +123,9 @@ def setup_case(args, rank, world):
     if w["n"] is not None:
         n = args.n or w["n"]
         overrides.update({"mesh.nx": n, "mesh.ny": n, "mesh.nz": n})
+        if getattr(args, "shape", None):  # per-GPU interior box, e.g. 1024,1024,128 (configs[3] on 8 GPUs)
+            sx, sy, sz = (int(v) for v in args.shape.split(","))
+            overrides.update({"mesh.nx": sx, "mesh.ny": sy, "mesh.nz": sz})
     overrides["run.noutput"] = 0
     case = hostapi.Case(os.path.join(ROOT, "euler_kokkos_b200", "settings", w["ini"]), overrides, rank=rank, nranks=world)
     return case, w
@@ -365,6 +368,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="blast3d", choices=sorted(WORKLOADS))
     ap.add_argument("--n", "--size", dest="n", type=int, default=None, help="cubic interior size per GPU (default 512); use --size under torchrun, whose own parser claims --n")
+    ap.add_argument("--shape", default=None, help="per-GPU interior box NX,NY,NZ of a 3-D workload (overrides --n)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:

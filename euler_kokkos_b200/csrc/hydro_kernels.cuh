@@ -50,9 +50,16 @@ struct HydroArgs {
   int zstep;  // ... and chunk stride per blockIdx.z (lets one launch take the two end chunks, another the middle ones)
 };
 
-template <int DIM, int RS, int TY, bool GRAV>
-__global__ void __launch_bounds__(32 * (TY + 4), 1) hydro_step_kernel(const HydroArgs a)
+// FOLD = 1 ("folded halo rows", 3-D): the CTA has one warp per row 1 .. TY+2 only.  Rows 0 and TY+3 of the tile
+// are never traced nor solved -- only their primitives are needed, as y neighbours of rows 1 and TY+2 -- so in the
+// FOLD = 0 layout their two warps (and the registers reserved for them) idle through every phase.  Here the warp of
+// row 1, which traces but solves no Riemann problem, converts those two rows while the other warps solve theirs.
+// With TY = 14 that is 16 warps of which 15 solve Riemann problems (4 per warp scheduler) on a 28 x 14 tile,
+// against 12 of 15 warps on a 28 x 11 tile.
+template <int DIM, int RS, int TY, bool GRAV, int FOLD = 0>
+__global__ void __launch_bounds__(32 * (TY + 4 - 2 * FOLD), 1) hydro_step_kernel(const HydroArgs a)
 {
+  static_assert(FOLD == 0 || DIM == 3, "folded halo rows: 3-D only");
   constexpr int NV = HydroTraits<DIM>::NV;
   using Smem = HydroSmem<DIM, TY>;
   constexpr int PLANE = Smem::PLANE;
@@ -65,7 +72,7 @@ __global__ void __launch_bounds__(32 * (TY + 4), 1) hydro_step_kernel(const Hydr
   const double dt = a.ts->dt;
   const double dtd[3] = { dt * g.invdx, dt * g.invdy, (DIM == 3) ? dt * g.invdz : 0.0 };
 
-  const int lane = threadIdx.x, row = threadIdx.y;
+  const int lane = threadIdx.x, row = threadIdx.y + FOLD;
   const int xg = g.gw + blockIdx.x * HTX + lane - 2; // ghosted coordinates of this thread's column
   const int yg = g.gw + blockIdx.y * TY + row - 2;
   const int so = row * 32 + lane; // offset inside one smem variable plane
@@ -96,6 +103,25 @@ __global__ void __launch_bounds__(32 * (TY + 4), 1) hydro_step_kernel(const Hydr
     for (int v = 0; v < NV; ++v)
       u[v] = inb ? __ldg(Uin + col + g.sk * k + g.sv * v) : 1.0;
   };
+  // FOLD: rows 0 and TY+3 of plane k, converted by the warp of row 1 (same columns, other rows)
+  const bool fold_warp = (FOLD != 0) && threadIdx.y == 0;
+  auto fold_rows_to_ring = [&](int k, int slot) {
+    const bool in0 = (xg < g.isize) && (yg - 1 < g.jsize), in3 = (xg < g.isize) && (yg + TY + 2 < g.jsize);
+    double u0[NV], u3[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      u0[v] = in0 ? __ldg(Uin + col - g.sj + g.sk * k + g.sv * v) : 1.0;
+      u3[v] = in3 ? __ldg(Uin + col + g.sj * (TY + 2) + g.sk * k + g.sv * v) : 1.0;
+    }
+    double q0[NV], q3[NV], rd;
+    hydro_cons_to_prim<DIM>(g, u0, q0, rd);
+    hydro_cons_to_prim<DIM>(g, u3, q3, rd);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      sm.q[slot][v * PLANE + so - 32] = q0[v];
+      sm.q[slot][v * PLANE + so + 32 * (TY + 2)] = q3[v];
+    }
+  };
 
   int kbeg = 0, kend = 1;
   if constexpr (DIM == 3) {
@@ -114,6 +140,11 @@ __global__ void __launch_bounds__(32 * (TY + 4), 1) hydro_step_kernel(const Hydr
       prims_to_ring(u, 1);
       load_u(kbeg, u);
       prims_to_ring(u, 2);
+      if (fold_warp) {
+        fold_rows_to_ring(kbeg - 2, 0);
+        fold_rows_to_ring(kbeg - 1, 1);
+        fold_rows_to_ring(kbeg, 2);
+      }
     } else {
       load_u(0, u);
       prims_to_ring(u, 0);
@@ -270,6 +301,10 @@ __global__ void __launch_bounds__(32 * (TY + 4), 1) hydro_step_kernel(const Hydr
             fl[2][v] = f[2][v] * dtd[2];
         }
       }
+    } else if (fold_warp && have_next) {
+      // rows 0 / TY+3 of plane p+2 into the ring slot of plane p-1: nobody reads those rows of that slot before
+      // plane p+2 is the centre plane, two iterations (four barriers) from now
+      fold_rows_to_ring(p + 2, sm1);
     }
     __syncthreads();
 
@@ -361,10 +396,10 @@ __global__ void __launch_bounds__(32 * (TY + 4), 1) hydro_step_kernel(const Hydr
   // -- CFL reduction for the NEXT step: warp shuffles, then one atomic per CTA (grid reduce)
   invdt = warp_max(invdt);
   if (lane == 0)
-    sm.red[row] = invdt;
+    sm.red[threadIdx.y] = invdt;
   __syncthreads();
-  if (row == 0) {
-    double m = (lane < TY + 4) ? sm.red[lane] : 0.0;
+  if (threadIdx.y == 0) {
+    double m = (lane < TY + 4 - 2 * FOLD) ? sm.red[lane] : 0.0;
     m = warp_max(m);
     if (lane == 0)
       atomic_max_nonneg(&a.ts->invdt_bits, m);

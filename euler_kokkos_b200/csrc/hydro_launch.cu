@@ -1,7 +1,9 @@
 // Host-side dispatch of the fused hydro step: picks the template instance (dimension, Riemann
 // solver, gravity) and sizes the grid for the 148 SMs of a B200.
 #include "ek_internal.h"
+#include <cstdlib>
 #include "hydro_kernels.cuh"
+#include "hydro_kernels_1b.cuh"
 
 namespace ek {
 
@@ -12,6 +14,33 @@ namespace ek {
 #define EK_HYDRO_TY 11
 #endif
 constexpr int TY = EK_HYDRO_TY;
+#ifndef EK_HYDRO_TYF
+// interior rows per tile of the 3-D "folded halo rows" layout (hydro_kernels.cuh): TYF+2 = 16 warps per CTA, the 15
+// that solve Riemann problems spread 4/4/4/3 over the warp schedulers and the row-1 warp rides with the 3
+#define EK_HYDRO_TYF 14
+#endif
+constexpr int TYF = EK_HYDRO_TYF;
+
+// 3-D tile layout: 1 = folded halo rows, 28 x 14 tile, 16 warps; 0 = one warp per tile row incl. halo rows, 28 x 11,
+// 15 warps.  Measured at 512^3 (profiles/r01_hydro_fold_ncu.txt): the folded layout executes 3.4 % fewer
+// instructions and halves the barrier stalls, but its 512 threads leave 128 registers per thread instead of 136, the
+// three lock-step HLLC problems interleave less (fixed-latency "wait" stalls 0.98 -> 1.93 per issue) and it ends 1.6 %
+// slower (10.90 vs 10.73 ms); with the iterative two-shock solver + gravity it is 8 % faster (34.5 vs 37.5 ms).
+// Default: folded for riemann = approx, unfolded otherwise; EK_HYDRO_FOLD=0/1 forces one.
+static bool use_fold(int riemann)
+{
+  const int v = getenv("EK_HYDRO_FOLD") ? atoi(getenv("EK_HYDRO_FOLD")) : -1;
+  return v < 0 ? riemann == RIEMANN_APPROX : v != 0;
+}
+
+// 3-D schedule: 0 (default) = two block barriers per plane (hydro_kernels.cuh); 1 = the one-barrier software
+// pipeline of hydro_kernels_1b.cuh (measured 1.7 % slower at 512^3: the barrier stalls ncu reports belong to the
+// halo-row warps, which have nothing else to do)
+static bool use_1b()
+{
+  const int v = getenv("EK_HYDRO_1B") ? atoi(getenv("EK_HYDRO_1B")) : 0;
+  return v != 0;
+}
 
 // z-chunk length: enough CTAs to fill whole waves over the SMs, long enough to amortise the
 // 3-plane pipeline warm-up of every chunk.
@@ -27,7 +56,7 @@ static int pick_zchunk(int nz, long long xy_ctas, int sm_count, int min_chunks =
     const long long ctas = xy_ctas * real_chunks;
     const long long waves = (ctas + sm_count - 1) / sm_count;
     const double tail = (double)(waves * sm_count) / (double)ctas; // idle-SM factor of the last wave
-    const double warm = (double)(zc + 2.5) / (double)zc;           // pipeline warm-up per chunk
+    const double warm = (double)(zc + (use_1b() ? 3.5 : 2.5)) / (double)zc; // pipeline warm-up per chunk
     const double cost = tail * warm;
     if (cost < best_cost - 1e-12) {
       best_cost = cost;
@@ -63,23 +92,44 @@ static ZPlan z_plan(const Ctx& c, long long xy_ctas, bool want_split)
   return z;
 }
 
-static long long hydro_xy_ctas(const Grid& g) { return (long long)((g.nx + HTX - 1) / HTX) * ((g.ny + TY - 1) / TY); }
+static int tile_rows(int dim, int riemann) { return (dim == 3 && use_fold(riemann) && !use_1b()) ? TYF : TY; }
+static long long hydro_xy_ctas(const Grid& g, int riemann)
+{
+  const int ty = tile_rows(g.nz > 1 ? 3 : 2, riemann);
+  return (long long)((g.nx + HTX - 1) / HTX) * ((g.ny + ty - 1) / ty);
+}
 
-bool hydro_z_splittable(const Ctx& c) { return c.p.dim == 3 && z_plan(c, hydro_xy_ctas(c.g), true).splittable; }
+bool hydro_z_splittable(const Ctx& c) { return c.p.dim == 3 && z_plan(c, hydro_xy_ctas(c.g, c.p.riemann), true).splittable; }
 
 // part: 0 = every chunk, 1 = the two end chunks, 2 = the middle chunks (1 and 2 only when splittable)
 template <int DIM, int RS, bool GRAV>
 static cudaError_t launch_one(Ctx& c, const double* Uin, double* Uout, int part, cudaStream_t stream)
 {
   using Smem = HydroSmem<DIM, TY>;
-  auto kern = hydro_step_kernel<DIM, RS, TY, GRAV>;
-  static bool attr_done[16] = { false };
-  const size_t smem = sizeof(Smem);
-  if (!attr_done[c.device & 15]) {
+  void (*kern)(const HydroArgs) = hydro_step_kernel<DIM, RS, TY, GRAV>;
+  size_t smem = sizeof(Smem);
+  if constexpr (DIM == 3 && RS != RIEMANN_HLL) {
+    if (use_1b()) {
+      kern = hydro_step1b_kernel<RS, TY, GRAV>;
+      smem = sizeof(HydroSmem1b<TY>);
+    }
+  }
+  int ty = TY, warps = TY + 4;
+  if constexpr (DIM == 3) {
+    if (tile_rows(3, RS) == TYF) {
+      kern = hydro_step_kernel<DIM, RS, TYF, GRAV, 1>;
+      smem = sizeof(HydroSmem<DIM, TYF>);
+      ty = TYF;
+      warps = TYF + 2;
+    }
+  }
+  const int variant = (ty == TYF && DIM == 3) ? 2 : (use_1b() ? 1 : 0);
+  static bool attr_done[16][3] = { { false } };
+  if (!attr_done[c.device & 15][variant]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess)
       return e;
-    attr_done[c.device & 15] = true;
+    attr_done[c.device & 15][variant] = true;
   }
   HydroArgs a;
   a.g = c.g;
@@ -87,8 +137,8 @@ static cudaError_t launch_one(Ctx& c, const double* Uin, double* Uout, int part,
   a.Uout = Uout;
   a.grav = c.grav;
   a.ts = c.ts;
-  dim3 block(32, TY + 4, 1);
-  dim3 grid((c.g.nx + HTX - 1) / HTX, (c.g.ny + TY - 1) / TY, 1);
+  dim3 block(32, warps, 1);
+  dim3 grid((c.g.nx + HTX - 1) / HTX, (c.g.ny + ty - 1) / ty, 1);
   a.zchunk = 1;
   a.zfirst = 0;
   a.zstep = 1;

@@ -167,15 +167,24 @@ EK_HD bool mhd_chunk_cell(const Grid& g, const MhdChunkMap& m, unsigned t, MhdId
 // Q(i,j,k) for 0 <= i < isize-1 (the last layer is never written, MHDRunFunctors3D.h:120-122);
 // returns the cell's inverse-dt contribution (0 outside the interior).
 // primitives of one cell (0 <= i < isize-1 etc., checked by the caller) into q[8]
-EK_HD void mhd_prims_at(const Grid& g, const double* __restrict__ U, const MhdIdx& x, double* __restrict__ q)
+// conserved state of one cell + the field on its three upper faces: u[0..7], u[8..10] (1.0 when !active)
+EK_HD void mhd_cons_load(const Grid& g, const double* __restrict__ U, const MhdIdx& x, bool active, double* __restrict__ u)
 {
   const double* __restrict__ Uc = U + x.c;
   const long long sv = g.sv;
-  double u[8];
 #pragma unroll
   for (int v = 0; v < 8; ++v)
-    u[v] = Uc[sv * v];
-  mhd_cons_to_prim(g, u, Uc[sv * IA + 1], Uc[sv * IB + x.sj], Uc[sv * IC + x.sk], q);
+    u[v] = active ? Uc[sv * v] : 1.0;
+  u[8] = active ? Uc[sv * IA + 1] : 1.0;
+  u[9] = active ? Uc[sv * IB + x.sj] : 1.0;
+  u[10] = active ? Uc[sv * IC + x.sk] : 1.0;
+}
+
+EK_HD void mhd_prims_at(const Grid& g, const double* __restrict__ U, const MhdIdx& x, double* __restrict__ q)
+{
+  double u[11];
+  mhd_cons_load(g, U, x, true, u);
+  mhd_cons_to_prim(g, u, u[8], u[9], u[10], q);
 }
 
 EK_HD double mhd_stage_prims(const Grid& g, const double* __restrict__ U, double* __restrict__ Q, const MhdIdx& x)
@@ -207,32 +216,57 @@ EK_HD bool mhd_elec_active(const Grid& g, const MhdIdx& x)
   return !(x.i < 1 || x.j < 1 || x.k < 1 || x.i > g.isize - 2 || x.j > g.jsize - 2 || x.k > g.ksize - 2);
 }
 
-// Ec: tile pointer of the output (Ex, Ey, Ez at Ec[0], Ec[TL], Ec[2*TL])
-EK_HD void mhd_elec_core(const Grid& g, const double* __restrict__ U, const MhdIdx& x, const MhdElecQ& P, double* __restrict__ Ec)
+// face-centred field values the three lower edges of a cell touch (conserved state U; loaded apart from the
+// arithmetic so that a kernel can issue the loads early)
+struct MhdElecB {
+  double A0, B0, C0, Aym, Azm, Bxm, Bzm, Cxm, Cym;
+};
+
+EK_HD void mhd_elec_load(const Grid& g, const double* __restrict__ U, const MhdIdx& x, bool active, MhdElecB& f)
 {
-  const unsigned c = x.c, sj = x.sj, sk = x.sk;
-  const long long sv = g.sv;
+  const long long sv = g.sv, sj = x.sj, sk = x.sk;
+  const double* __restrict__ UA = U + sv * IA + x.c;
+  const double* __restrict__ UB = U + sv * IB + x.c;
+  const double* __restrict__ UC = U + sv * IC + x.c;
+  f.A0 = active ? UA[0] : 0.0;
+  f.B0 = active ? UB[0] : 0.0;
+  f.C0 = active ? UC[0] : 0.0;
+  f.Aym = active ? UA[-sj] : 0.0;
+  f.Azm = active ? UA[-sk] : 0.0;
+  f.Bxm = active ? UB[-1] : 0.0;
+  f.Bzm = active ? UB[-sk] : 0.0;
+  f.Cxm = active ? UC[-1] : 0.0;
+  f.Cym = active ? UC[-sj] : 0.0;
+}
+
+// Ec: tile pointer of the output (Ex, Ey, Ez at Ec[0], Ec[TL], Ec[2*TL])
+EK_HD void mhd_elec_core(const MhdElecB& f, const MhdElecQ& P, double* __restrict__ Ec)
+{
   const double *q000 = P.q000, *q100 = P.q100, *q010 = P.q010, *q001 = P.q001, *q110 = P.q110, *q101 = P.q101, *q011 = P.q011;
-  const double* __restrict__ UA = U + sv * IA + c;
-  const double* __restrict__ UB = U + sv * IB + c;
-  const double* __restrict__ UC = U + sv * IC + c;
-  const double A0 = UA[0], B0 = UB[0], C0 = UC[0];
+  const double A0 = f.A0, B0 = f.B0, C0 = f.C0;
   double u, v, w, A, B, C;
   v = 0.25 * (q011[TL * IV] + q010[TL * IV] + q001[TL * IV] + q000[TL * IV]);
   w = 0.25 * (q011[TL * IW] + q010[TL * IW] + q001[TL * IW] + q000[TL * IW]);
-  B = 0.5 * (UB[-(long long)sk] + B0);
-  C = 0.5 * (UC[-(long long)sj] + C0);
+  B = 0.5 * (f.Bzm + B0);
+  C = 0.5 * (f.Cym + C0);
   Ec[0] = v * C - w * B;
   u = 0.25 * (q101[TL * IU] + q100[TL * IU] + q001[TL * IU] + q000[TL * IU]);
   w = 0.25 * (q101[TL * IW] + q100[TL * IW] + q001[TL * IW] + q000[TL * IW]);
-  A = 0.5 * (UA[-(long long)sk] + A0);
-  C = 0.5 * (UC[-1] + C0);
+  A = 0.5 * (f.Azm + A0);
+  C = 0.5 * (f.Cxm + C0);
   Ec[TL] = w * A - u * C;
   u = 0.25 * (q110[TL * IU] + q100[TL * IU] + q010[TL * IU] + q000[TL * IU]);
   v = 0.25 * (q110[TL * IV] + q100[TL * IV] + q010[TL * IV] + q000[TL * IV]);
-  A = 0.5 * (UA[-(long long)sj] + A0);
-  B = 0.5 * (UB[-1] + B0);
+  A = 0.5 * (f.Aym + A0);
+  B = 0.5 * (f.Bxm + B0);
   Ec[2 * TL] = u * B - v * A;
+}
+
+EK_HD void mhd_elec_core(const Grid& g, const double* __restrict__ U, const MhdIdx& x, const MhdElecQ& P, double* __restrict__ Ec)
+{
+  MhdElecB f;
+  mhd_elec_load(g, U, x, true, f);
+  mhd_elec_core(f, P, Ec);
 }
 
 EK_HD void mhd_stage_elec(const Grid& g, const double* __restrict__ U, const double* __restrict__ Q, double* __restrict__ E,
@@ -267,20 +301,50 @@ EK_HD bool mhd_trace_active(const Grid& g, const MhdIdx& x)
   return !(x.i < 2 || x.j < 2 || x.k < 2 || x.i > g.isize - 2 || x.j > g.jsize - 2 || x.k > g.ksize - 2);
 }
 
+// face-centred field values the predictor of one cell reads from the conserved state U: the cell's own lower
+// faces and their neighbours along the two transverse directions and along the normal (loaded apart from the
+// arithmetic so that a kernel can issue the loads early); all of them exist for an active cell (2 <= i <= isize-2)
+struct MhdTraceB {
+  double A0, Axp, Aym, Ayp, Azm, Azp;
+  double B0, Bxm, Bxp, Byp, Bzm, Bzp;
+  double C0, Cxm, Cxp, Cym, Cyp, Czp;
+};
+
+EK_HD void mhd_trace_load(const Grid& g, const double* __restrict__ U, const MhdIdx& x, bool active, MhdTraceB& f)
+{
+  const long long sj = x.sj, sk = x.sk, sv = g.sv;
+  const double* __restrict__ UA = U + sv * IA + x.c;
+  const double* __restrict__ UB = U + sv * IB + x.c;
+  const double* __restrict__ UC = U + sv * IC + x.c;
+  f.A0 = active ? UA[0] : 0.0;
+  f.Axp = active ? UA[1] : 0.0;
+  f.Aym = active ? UA[-sj] : 0.0;
+  f.Ayp = active ? UA[sj] : 0.0;
+  f.Azm = active ? UA[-sk] : 0.0;
+  f.Azp = active ? UA[sk] : 0.0;
+  f.B0 = active ? UB[0] : 0.0;
+  f.Bxm = active ? UB[-1] : 0.0;
+  f.Bxp = active ? UB[1] : 0.0;
+  f.Byp = active ? UB[sj] : 0.0;
+  f.Bzm = active ? UB[-sk] : 0.0;
+  f.Bzp = active ? UB[sk] : 0.0;
+  f.C0 = active ? UC[0] : 0.0;
+  f.Cxm = active ? UC[-1] : 0.0;
+  f.Cxp = active ? UC[1] : 0.0;
+  f.Cym = active ? UC[-sj] : 0.0;
+  f.Cyp = active ? UC[sj] : 0.0;
+  f.Czp = active ? UC[sk] : 0.0;
+}
+
 // Sc: tile pointer of the cell's compact state (output)
-EK_HD void mhd_trace_core(const Grid& g, const double* __restrict__ U, const MhdTraceIn& P, double* __restrict__ Sc, double dtdx,
+EK_HD void mhd_trace_core(const Grid& g, const MhdTraceB& fb, const MhdTraceIn& P, double* __restrict__ Sc, double dtdx,
                           double dtdy, double dtdz, const MhdIdx& x)
 {
-  const unsigned c = x.c;
-  const long long sj = x.sj, sk = x.sk, sv = g.sv;
-  const double* __restrict__ UA = U + sv * IA + c;
-  const double* __restrict__ UB = U + sv * IB + c;
-  const double* __restrict__ UC = U + sv * IC + c;
   const double* __restrict__ E0 = P.E0;
   const bool in_i = x.i <= g.isize - 3, in_j = x.j <= g.jsize - 3, in_k = x.k <= g.ksize - 3;
   const double xst = dmin(g.slope_type, 2.0); // slope_unsplit_mhd_3d, MHDBaseFunctor3D.h:600
 
-  const double AL = UA[0], BL = UB[0], CL = UC[0];
+  const double AL = fb.A0, BL = fb.B0, CL = fb.C0;
   const double ELL = E0[0], FLL = E0[TL], GLL = E0[2 * TL];
   const double* __restrict__ Ei = P.Ei;
   const double* __restrict__ Ej = P.Ej;
@@ -289,20 +353,20 @@ EK_HD void mhd_trace_core(const Grid& g, const double* __restrict__ U, const Mhd
   if (in_j && in_k) {
     const double GLR = Ej[2 * TL], FLR = Ek[TL];
     Sc[TL * SFA] = AL + (+(GLR - GLL) * dtdy * 0.5 - (FLR - FLL) * dtdz * 0.5);
-    Sc[TL * SDAY] = mhd_half_slope(0.5 * xst, g.slope_k, UA[-sj], AL, UA[sj]);
-    Sc[TL * SDAZ] = mhd_half_slope(0.5 * xst, g.slope_k, UA[-sk], AL, UA[sk]);
+    Sc[TL * SDAY] = mhd_half_slope(0.5 * xst, g.slope_k, fb.Aym, AL, fb.Ayp);
+    Sc[TL * SDAZ] = mhd_half_slope(0.5 * xst, g.slope_k, fb.Azm, AL, fb.Azp);
   }
   if (in_i && in_k) {
     const double GRL = Ei[2 * TL], ELR = Ek[0];
     Sc[TL * SFB] = BL + (-(GRL - GLL) * dtdx * 0.5 + (ELR - ELL) * dtdz * 0.5);
-    Sc[TL * SDBX] = mhd_half_slope(0.5 * xst, g.slope_k, UB[-1], BL, UB[1]);
-    Sc[TL * SDBZ] = mhd_half_slope(0.5 * xst, g.slope_k, UB[-sk], BL, UB[sk]);
+    Sc[TL * SDBX] = mhd_half_slope(0.5 * xst, g.slope_k, fb.Bxm, BL, fb.Bxp);
+    Sc[TL * SDBZ] = mhd_half_slope(0.5 * xst, g.slope_k, fb.Bzm, BL, fb.Bzp);
   }
   if (in_i && in_j) {
     const double FRL = Ei[TL], ERL = Ej[0];
     Sc[TL * SFC] = CL + (+(FRL - FLL) * dtdx * 0.5 - (ERL - ELL) * dtdy * 0.5);
-    Sc[TL * SDCX] = mhd_half_slope(0.5 * xst, g.slope_k, UC[-1], CL, UC[1]);
-    Sc[TL * SDCY] = mhd_half_slope(0.5 * xst, g.slope_k, UC[-sj], CL, UC[sj]);
+    Sc[TL * SDCX] = mhd_half_slope(0.5 * xst, g.slope_k, fb.Cxm, CL, fb.Cxp);
+    Sc[TL * SDCY] = mhd_half_slope(0.5 * xst, g.slope_k, fb.Cym, CL, fb.Cyp);
   }
   if (!(in_i && in_j && in_k))
     return;
@@ -329,7 +393,7 @@ EK_HD void mhd_trace_core(const Grid& g, const double* __restrict__ U, const Mhd
     for (int n = 0; n < 8; ++n)
       d[n] = (use_slopes && n != IA) ? mhd_half_slope(sth, g.slope_k, Qm[TL * n], q[n], Qp[TL * n]) : 0.0;
     const double drx = d[ID], dpx = d[IP], dux = d[IU], dvx = d[IV], dwx = d[IW], dBx = d[IB], dCx = d[IC];
-    const double dAx = 0.5 * (UA[1] - AL);
+    const double dAx = 0.5 * (fb.Axp - AL);
     sr0 = (-u * drx - dux * r) * dtdx;
     su0 = (-u * dux - (dpx + B * dBx + C * dCx) * ir) * dtdx;
     sv0 = (-u * dvx + A * dBx * ir) * dtdx;
@@ -348,7 +412,7 @@ EK_HD void mhd_trace_core(const Grid& g, const double* __restrict__ U, const Mhd
     for (int n = 0; n < 8; ++n)
       d[n] = (use_slopes && n != IB) ? mhd_half_slope(sth, g.slope_k, Qm[TL * n], q[n], Qp[TL * n]) : 0.0;
     const double dry = d[ID], dpy = d[IP], duy = d[IU], dvy = d[IV], dwy = d[IW], dAy = d[IA], dCy = d[IC];
-    const double dBy = 0.5 * (UB[sj] - BL);
+    const double dBy = 0.5 * (fb.Byp - BL);
     sr0 += (-v * dry - dvy * r) * dtdy;
     su0 += (-v * duy + B * dAy * ir) * dtdy;
     sv0 += (-v * dvy - (dpy + A * dAy + C * dCy) * ir) * dtdy;
@@ -367,7 +431,7 @@ EK_HD void mhd_trace_core(const Grid& g, const double* __restrict__ U, const Mhd
     for (int n = 0; n < 8; ++n)
       d[n] = (use_slopes && n != IC) ? mhd_half_slope(sth, g.slope_k, Qm[TL * n], q[n], Qp[TL * n]) : 0.0;
     const double drz = d[ID], dpz = d[IP], duz = d[IU], dvz = d[IV], dwz = d[IW], dAz = d[IA], dBz = d[IB];
-    const double dCz = 0.5 * (UC[sk] - CL);
+    const double dCz = 0.5 * (fb.Czp - CL);
     sr0 += (-w * drz - dwz * r) * dtdz;
     su0 += (-w * duz + C * dAz * ir) * dtdz;
     sv0 += (-w * dvz + C * dBz * ir) * dtdz;
@@ -386,6 +450,14 @@ EK_HD void mhd_trace_core(const Grid& g, const double* __restrict__ U, const Mhd
   Sc[TL * (SC + IA)] = A + sA0;
   Sc[TL * (SC + IB)] = B + sB0;
   Sc[TL * (SC + IC)] = C + sC0;
+}
+
+EK_HD void mhd_trace_core(const Grid& g, const double* __restrict__ U, const MhdTraceIn& P, double* __restrict__ Sc, double dtdx,
+                          double dtdy, double dtdz, const MhdIdx& x)
+{
+  MhdTraceB fb;
+  mhd_trace_load(g, U, x, true, fb);
+  mhd_trace_core(g, fb, P, Sc, dtdx, dtdy, dtdz, x);
 }
 
 EK_HD void mhd_stage_trace(const Grid& g, const double* __restrict__ U, const double* __restrict__ Q, const double* __restrict__ E,

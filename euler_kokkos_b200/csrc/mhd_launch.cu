@@ -119,7 +119,8 @@ static cudaError_t launch_step(Ctx& c, const double* Uin, double* Uout, int part
     }
     const int zchunk = (nplanes + nchunk - 1) / nchunk;
     grid.z = (nplanes + zchunk - 1) / zchunk;
-    mhd_pet_kernel<0><<<grid, PET_TX * PET_TY, sizeof(PetSmem), c.stream>>>(a, zchunk);
+    static const int pet_pf = getenv("EK_MHD_PET_PF") ? atoi(getenv("EK_MHD_PET_PF")) : 0; // L2 prefetch of the plane converted next
+    mhd_pet_kernel<0><<<grid, PET_TX * PET_TY, sizeof(PetSmem), c.stream>>>(a, zchunk, pet_pf);
     c.launches++;
     c.mhd_prims_of = nullptr;
   } else {

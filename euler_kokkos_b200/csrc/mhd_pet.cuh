@@ -24,7 +24,7 @@ struct PetSmem {
 };
 
 template <int DUMMY = 0>
-__global__ void __launch_bounds__(PET_TX* PET_TY, 2) mhd_pet_kernel(const MhdArgs a, const int zchunk)
+__global__ void __launch_bounds__(PET_TX* PET_TY, 2) mhd_pet_kernel(const MhdArgs a, const int zchunk, const int l2_prefetch)
 {
   extern __shared__ __align__(16) unsigned char pet_raw[];
   PetSmem& sm = *reinterpret_cast<PetSmem*>(pet_raw);
@@ -51,66 +51,127 @@ __global__ void __launch_bounds__(PET_TX* PET_TY, 2) mhd_pet_kernel(const MhdArg
     x.sk = sk;
     x.c = (unsigned)x.i + sj * (unsigned)x.j + sk * (unsigned)k;
   };
-  // primitives of the box cells of plane k -> ring slot k & 3 (cells the reference never converts are skipped)
+  constexpr int NT = PET_TX * PET_TY;
+  static_assert(PET_BOX > NT && PET_BOX <= 2 * NT, "the staging passes below are written for two passes over the box");
+  // this thread's two box cells in the staging passes (the second one exists for the first PET_BOX - NT threads)
+  const int bA = t, bB = t + NT;
+  const bool hasB = bB < PET_BOX;
+
+  // primitives of the box cells of plane k -> ring slot k & 3 (cells the reference never converts are skipped);
+  // the loads of both passes are issued before the first conversion
   auto prims_plane = [&](int k) {
     if (k >= g.ksize - 1)
       return;
     double* __restrict__ qs = sm.q[k & 3];
-    for (int b = t; b < PET_BOX; b += PET_TX * PET_TY) {
-      MhdIdx x;
-      cell_of_box(b, k, x);
-      if (x.i >= g.isize - 1 || x.j >= g.jsize - 1)
-        continue;
+    MhdIdx xA, xB;
+    cell_of_box(bA, k, xA);
+    cell_of_box(hasB ? bB : bA, k, xB);
+    const bool okA = xA.i < g.isize - 1 && xA.j < g.jsize - 1;
+    const bool okB = hasB && xB.i < g.isize - 1 && xB.j < g.jsize - 1;
+    double uA[11], uB[11];
+    mhd_cons_load(g, a.Uin, xA, okA, uA);
+    mhd_cons_load(g, a.Uin, xB, okB, uB);
+    if (okA) {
       double q[8];
-      mhd_prims_at(g, a.Uin, x, q);
-      double* __restrict__ qc = qs + tile_off<8>((unsigned)b);
+      mhd_cons_to_prim(g, uA, uA[8], uA[9], uA[10], q);
+      double* __restrict__ qc = qs + tile_off<8>((unsigned)bA);
+#pragma unroll
+      for (int v = 0; v < 8; ++v)
+        qc[TL * v] = q[v];
+    }
+    if (okB) {
+      double q[8];
+      mhd_cons_to_prim(g, uB, uB[8], uB[9], uB[10], q);
+      double* __restrict__ qc = qs + tile_off<8>((unsigned)bB);
 #pragma unroll
       for (int v = 0; v < 8; ++v)
         qc[TL * v] = q[v];
     }
   };
-  // edge field of plane k (needs the primitives of planes k-1 and k) -> slot k & 1
-  auto elec_plane = [&](int k) {
-    if (k > g.ksize - 2)
+  // edge field of plane k (needs the primitives of planes k-1 and k) -> slot k & 1.  The face-centred field values
+  // come from the conserved state: elec_load issues those loads (before the barrier that publishes the primitives),
+  // elec_plane does the arithmetic after it.
+  auto elec_cell = [&](int b, int k, MhdIdx& x) {
+    const int bj = b / PET_BX, bi = b - bj * PET_BX;
+    cell_of_box(b, k, x);
+    return k <= g.ksize - 2 && bi >= 1 && bj >= 1 && mhd_elec_active(g, x);
+  };
+  auto elec_load = [&](int k, MhdElecB& fA, MhdElecB& fB) {
+    MhdIdx x;
+    const bool okA = elec_cell(bA, k, x);
+    mhd_elec_load(g, a.Uin, x, okA, fA);
+    const bool okB = hasB && elec_cell(hasB ? bB : bA, k, x);
+    mhd_elec_load(g, a.Uin, x, okB, fB);
+  };
+  auto elec_one = [&](int b, int k, const MhdElecB& f) {
+    MhdIdx x;
+    if (!elec_cell(b, k, x))
       return;
     const double* __restrict__ q0 = sm.q[k & 3];
     const double* __restrict__ qm = sm.q[(k - 1) & 3];
-    double* __restrict__ es = sm.e[k & 1];
-    for (int b = t; b < PET_BOX; b += PET_TX * PET_TY) {
-      const int bj = b / PET_BX, bi = b - bj * PET_BX;
-      if (bi < 1 || bj < 1)
-        continue;
-      MhdIdx x;
-      cell_of_box(b, k, x);
-      if (!mhd_elec_active(g, x))
-        continue;
-      MhdElecQ P;
-      P.q000 = q0 + tile_off<8>((unsigned)b);
-      P.q100 = q0 + tile_off<8>((unsigned)(b - 1));
-      P.q010 = q0 + tile_off<8>((unsigned)(b - PET_BX));
-      P.q110 = q0 + tile_off<8>((unsigned)(b - 1 - PET_BX));
-      P.q001 = qm + tile_off<8>((unsigned)b);
-      P.q101 = qm + tile_off<8>((unsigned)(b - 1));
-      P.q011 = qm + tile_off<8>((unsigned)(b - PET_BX));
-      mhd_elec_core(g, a.Uin, x, P, es + tile_off<3>((unsigned)b));
-    }
+    MhdElecQ P;
+    P.q000 = q0 + tile_off<8>((unsigned)b);
+    P.q100 = q0 + tile_off<8>((unsigned)(b - 1));
+    P.q010 = q0 + tile_off<8>((unsigned)(b - PET_BX));
+    P.q110 = q0 + tile_off<8>((unsigned)(b - 1 - PET_BX));
+    P.q001 = qm + tile_off<8>((unsigned)b);
+    P.q101 = qm + tile_off<8>((unsigned)(b - 1));
+    P.q011 = qm + tile_off<8>((unsigned)(b - PET_BX));
+    mhd_elec_core(f, P, sm.e[k & 1] + tile_off<3>((unsigned)b));
   };
-
-  prims_plane(kbeg - 1);
-  prims_plane(kbeg);
-  prims_plane(kbeg + 1);
-  __syncthreads();
-  elec_plane(kbeg);
-  elec_plane(kbeg + 1);
-  __syncthreads();
+  auto elec_plane = [&](int k, const MhdElecB& fA, const MhdElecB& fB) {
+    elec_one(bA, k, fA);
+    if (hasB)
+      elec_one(bB, k, fB);
+  };
 
   const int lx = t & (PET_TX - 1), ly = t / PET_TX;
   const int bt = (1 + lx) + PET_BX * (1 + ly); // this thread's cell inside the box
+  // face-centred field values of the predictor of plane k (conserved state, 18 loads)
+  auto trace_cell = [&](int k, MhdIdx& x) {
+    cell_of_box(bt, k, x);
+    return x.i <= g.isize - 2 && x.j <= g.jsize - 2 && mhd_trace_active(g, x);
+  };
+
+  MhdElecB eA, eB;
+  MhdTraceB fb;
+  prims_plane(kbeg - 1);
+  prims_plane(kbeg);
+  prims_plane(kbeg + 1);
+  elec_load(kbeg, eA, eB);
+  __syncthreads();
+  elec_plane(kbeg, eA, eB);
+  elec_load(kbeg + 1, eA, eB);
+  elec_plane(kbeg + 1, eA, eB);
+  {
+    MhdIdx x;
+    const bool act = trace_cell(kbeg, x);
+    mhd_trace_load(g, a.Uin, x, act, fb);
+  }
+  __syncthreads();
+
   for (int p = kbeg; p < kend; ++p) {
+    if (l2_prefetch && p + 3 < g.ksize - 1) {
+      // the conserved state this thread converts next iteration: ask L2 for it now (first touch comes from DRAM)
+      MhdIdx x;
+      cell_of_box(bA, p + 3, x);
+      if (x.i < g.isize && x.j < g.jsize) {
+#pragma unroll
+        for (int v = 0; v < 8; ++v)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.Uin + g.sv * v + x.c));
+      }
+      if (hasB) {
+        cell_of_box(bB, p + 3, x);
+        if (x.i < g.isize && x.j < g.jsize) {
+#pragma unroll
+          for (int v = 0; v < 8; ++v)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.Uin + g.sv * v + x.c));
+        }
+      }
+    }
     {
       MhdIdx x;
-      cell_of_box(bt, p, x);
-      if (x.i <= g.isize - 2 && x.j <= g.jsize - 2 && mhd_trace_active(g, x)) {
+      if (trace_cell(p, x)) {
         const double* __restrict__ q0 = sm.q[p & 3];
         const double* __restrict__ e0 = sm.e[p & 1];
         MhdTraceIn P;
@@ -125,13 +186,20 @@ __global__ void __launch_bounds__(PET_TX* PET_TY, 2) mhd_pet_kernel(const MhdArg
         P.Ei = e0 + tile_off<3>((unsigned)(bt + 1));
         P.Ej = e0 + tile_off<3>((unsigned)(bt + PET_BX));
         P.Ek = sm.e[(p + 1) & 1] + tile_off<3>((unsigned)bt);
-        mhd_trace_core(g, a.Uin, P, w.S + tile_off<S_TOTAL>(x.c), dtdx, dtdy, dtdz, x);
+        mhd_trace_core(g, fb, P, w.S + tile_off<S_TOTAL>(x.c), dtdx, dtdy, dtdz, x);
       }
     }
     if (p + 1 < kend) {
+      // the next plane's field values are requested now and consumed after the two barriers below
+      {
+        MhdIdx x;
+        const bool act = trace_cell(p + 1, x);
+        mhd_trace_load(g, a.Uin, x, act, fb);
+      }
       prims_plane(p + 2); // slot (p+2)&3 held plane p-2: free
+      elec_load(p + 2, eA, eB);
       __syncthreads();
-      elec_plane(p + 2);  // slot p&1 held plane p: its readers passed the barrier above
+      elec_plane(p + 2, eA, eB); // slot p&1 held plane p: its readers passed the barrier above
       __syncthreads();
     }
   }

@@ -40,6 +40,17 @@ def test_hydro3d_one_step_parity(riemann, n):
     _check_steps(p, util.random_hydro_state(p, seed=1), 3)
 
 
+@pytest.mark.parametrize("knobs", [{"EK_HYDRO_FOLD": "0"}, {"EK_HYDRO_FOLD": "1"}, {"EK_HYDRO_1B": "1"}])
+@pytest.mark.parametrize("riemann", ["hllc", "approx", "llf"])
+def test_hydro3d_kernel_variants_agree_with_the_oracle(knobs, riemann, monkeypatch):
+    """every selectable 3-D schedule (one warp per tile row, folded halo rows, one barrier per plane) is held to the
+    same one-step tolerance, with reflective / outflow / periodic faces and several z chunks."""
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    p = util.make_params(dim=3, n=(61, 33, 40), riemann=riemann, bc=(3, 3, 1, 2, 2, 1))
+    _check_steps(p, util.random_hydro_state(p, seed=11), 2)
+
+
 @pytest.mark.parametrize("bc", [(1, 1, 1, 1, 1, 1), (2, 2, 2, 2, 2, 2), (3, 3, 3, 3, 3, 3), (3, 3, 1, 2, 2, 1)])
 def test_hydro3d_boundaries(bc):
     p = util.make_params(dim=3, n=(20, 14, 10), bc=bc)
