@@ -212,16 +212,33 @@ static int fill_boundaries(Ctx& c, double* U)
   return EK_OK;
 }
 
+// MHD: max invDt of the ghost-filled level U into ts->invdt_bits.  When the update kernel that produced U has already
+// reduced every interior cell but the last layers (mhd_dt_partial_for == U), only those layers are left.
+static int mhd_local_invdt(Ctx& c, const double* U)
+{
+  if (c.mhd_dt_partial_for == U && mhd_dt_folded(c)) {
+    EK_CUDA(&c, launch_mhd_invdt_layers(c, U));
+  } else {
+    EK_CUDA(&c, cudaMemsetAsync(&c.ts->invdt_bits, 0, sizeof(unsigned long long), c.stream));
+    EK_CUDA(&c, launch_mhd_invdt(c, U));
+  }
+  // the all-reduce that follows leaves the GLOBAL maximum in invdt_bits: still a valid starting value for a repeated
+  // call on the same level (a maximum is idempotent), so mhd_dt_partial_for stays
+  return EK_OK;
+}
+
 // max invDt of the current level into ts->invdt_bits (+ max over ranks)
 static int prime_invdt(Ctx& c)
 {
-  EK_CUDA(&c, cudaMemsetAsync(&c.ts->invdt_bits, 0, sizeof(unsigned long long), c.stream));
   if (c.p.mhd) {
     int rc = fill_boundaries(c, c.U[c.cur]); // MHD dt reads primitives that need the upper ghost faces
     if (rc != EK_OK)
       return rc;
-    EK_CUDA(&c, launch_mhd_invdt(c, c.U[c.cur]));
+    rc = mhd_local_invdt(c, c.U[c.cur]);
+    if (rc != EK_OK)
+      return rc;
   } else {
+    EK_CUDA(&c, cudaMemsetAsync(&c.ts->invdt_bits, 0, sizeof(unsigned long long), c.stream));
     EK_CUDA(&c, launch_hydro_invdt(c, c.U[c.cur]));
   }
   int rc = comm_allreduce_invdt(c);
@@ -242,14 +259,16 @@ static int enqueue_step(Ctx& c, int use_host_dt, double host_dt, int max_steps)
     if (rc != EK_OK)
       return rc;
     if (!use_host_dt) {
-      EK_CUDA(&c, cudaMemsetAsync(&c.ts->invdt_bits, 0, sizeof(unsigned long long), c.stream));
-      EK_CUDA(&c, launch_mhd_invdt(c, Uin));
+      rc = mhd_local_invdt(c, Uin);
+      if (rc != EK_OK)
+        return rc;
       rc = comm_allreduce_invdt(c);
       if (rc != EK_OK)
         return rc;
     }
-    pre_step_kernel<<<1, 1, 0, c.stream>>>(c.ts, c.p.cfl, use_host_dt, host_dt);
+    pre_step_kernel<<<1, 1, 0, c.stream>>>(c.ts, c.p.cfl, use_host_dt, host_dt); // zeroes invdt_bits
     c.launches++;
+    c.mhd_dt_partial_for = mhd_dt_folded(c) ? Uout : nullptr; // the update kernel reduces the new level
     ktime_mark(c);
     if (c.overlap_ok) {
       // every stage, the update of the END planes first; they travel to the z neighbours beside the update of the rest
@@ -450,6 +469,7 @@ int ek_upload_state(ek_ctx* ctx, const double* U_host)
   EK_CUDA(c, cudaMemcpyAsync(c->U[1], c->U[0], bytes, cudaMemcpyDeviceToDevice, c->stream));
   c->dt_primed = false;
   c->mhd_prims_of = nullptr;
+  c->mhd_dt_partial_for = nullptr;
   c->halo_ready_for = nullptr;
   EK_CUDA(c, cudaStreamSynchronize(c->stream)); // the host buffer may be pageable / reused
   return EK_OK;
@@ -472,6 +492,7 @@ int ek_device_state(ek_ctx* ctx, double** dptr)
   *dptr = c->U[c->cur];
   c->dt_primed = false; // the caller may modify the state through this pointer
   c->mhd_prims_of = nullptr;
+  c->mhd_dt_partial_for = nullptr;
   c->halo_ready_for = nullptr;
   return EK_OK;
 }
@@ -559,6 +580,7 @@ int ek_run(ek_ctx* ctx, int nsteps, double t, double t_end, double* t_out, doubl
   if (done < nsteps) {
     c->dt_primed = false; // skipped steps consumed nothing, but be conservative
     c->halo_ready_for = nullptr;
+    c->mhd_dt_partial_for = nullptr;
   }
   if (t_out) *t_out = c->ts_host->t;
   if (dt_last_out) *dt_last_out = c->ts_host->dt;

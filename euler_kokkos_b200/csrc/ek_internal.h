@@ -36,6 +36,8 @@ struct Ctx {
   int64_t launches = 0;
   bool dt_primed = false; // ts->invdt_bits holds max invDt of the current level
   const double* mhd_prims_of = nullptr; // level whose primitives currently sit in the MHD work area
+  // level whose CFL maximum (all interior cells but the last layers) the update kernel has left in ts->invdt_bits
+  const double* mhd_dt_partial_for = nullptr;
   int sm_count = 148;
   // communicator (z-slab / cartesian neighbours)
   void* nccl_comm = nullptr;
@@ -68,6 +70,8 @@ cudaError_t launch_hydro_invdt(Ctx& c, const double* U);
 // mhd_launch.cu
 cudaError_t launch_mhd_step(Ctx& c, const double* Uin, double* Uout, int part = 0);
 cudaError_t launch_mhd_invdt(Ctx& c, const double* U);
+cudaError_t launch_mhd_invdt_layers(Ctx& c, const double* U);
+bool mhd_dt_folded(const Ctx& c);
 size_t mhd_work_bytes(const Grid& g);
 // ek_comm.cu
 int comm_exchange_dir(Ctx& c, double* U, int dir, cudaStream_t stream = nullptr); // halo exchange along one direction

@@ -642,12 +642,20 @@ EK_HD void mhd_stage_emfs(const Grid& g, const double* __restrict__ S, double* _
 
 // ---- stage U ------------------------------------------------------------------------------------
 // UpdateFunctor3D_MHD + UpdateEmfFunctor3D on one interior cell, same accumulation order
-EK_HD void mhd_stage_update(const Grid& g, const double* __restrict__ Uin, const double* __restrict__ F, const double* __restrict__ EMF,
-                            double* __restrict__ Uout, double dtdx, double dtdy, double dtdz, const MhdIdx& x)
+// WANT_INVDT: also return the cell's inverse-dt contribution for the NEXT step (ComputeDtFunctor3D_MHD on the new
+// state, MHDRunFunctors3D.h:16-86) when it can be formed here: the cell-centred field needs the NEW field on the
+// cell's three upper faces, which the +x/+y/+z neighbours own; for neighbours that are interior cells the same CT
+// update is repeated here (same expression, same operand order: the value is the one the neighbour stores).  Cells of
+// the last interior layer along x, y or z return 0: their upper faces are ghosts, set by the boundary fill / halo
+// exchange that follows the step (mhd_invdt_layers_kernel takes those cells afterwards).
+template <bool WANT_INVDT>
+EK_HD double mhd_stage_update_t(const Grid& g, const double* __restrict__ Uin, const double* __restrict__ F,
+                                const double* __restrict__ EMF, double* __restrict__ Uout, double dtdx, double dtdy, double dtdz,
+                                const MhdIdx& x)
 {
   const int gw = g.gw;
   if (x.i < gw || x.j < gw || x.k < gw || x.i >= g.isize - gw || x.j >= g.jsize - gw || x.k >= g.ksize - gw)
-    return;
+    return 0.0;
   const unsigned c = x.c;
   const long long sv = g.sv;
   const double* __restrict__ F0 = F + tile_off<15>(c);
@@ -656,6 +664,7 @@ EK_HD void mhd_stage_update(const Grid& g, const double* __restrict__ Uin, const
   const double* __restrict__ Fk = F + tile_off<15>(c + x.sk);
   const double* __restrict__ Uc = Uin + c;
   double* __restrict__ Oc = Uout + c;
+  double un[8];
 #pragma unroll
   for (int v = 0; v < 5; ++v) {
     double u = Uc[sv * v];
@@ -666,6 +675,7 @@ EK_HD void mhd_stage_update(const Grid& g, const double* __restrict__ Uin, const
     u += F0[TL * (10 + v)] * dtdz;
     u -= Fk[TL * (10 + v)] * dtdz;
     Oc[sv * v] = u;
+    un[v] = u;
   }
   const double* __restrict__ E0 = EMF + tile_off<3>(c);
   const double* __restrict__ Ei = EMF + tile_off<3>(c + 1);
@@ -682,6 +692,43 @@ EK_HD void mhd_stage_update(const Grid& g, const double* __restrict__ Uin, const
   Oc[sv * IA] = A;
   Oc[sv * IB] = B;
   Oc[sv * IC] = C;
+  if constexpr (!WANT_INVDT)
+    return 0.0;
+  if (x.i >= g.isize - gw - 1 || x.j >= g.jsize - gw - 1 || x.k >= g.ksize - gw - 1)
+    return 0.0;
+  // the new field on the three upper faces = lower faces of the +x / +y / +z neighbours
+  const unsigned sj = x.sj, sk = x.sk;
+  double A1 = Uc[sv * IA + 1], B1 = Uc[sv * IB + sj], C1 = Uc[sv * IC + sk];
+  {
+    const double* __restrict__ Ejn = EMF + tile_off<3>(c + 1 + sj);
+    const double* __restrict__ Ekn = EMF + tile_off<3>(c + 1 + sk);
+    A1 += (Ejn[2 * TL] - Ei[2 * TL]) * dtdy;
+    A1 -= (Ekn[TL] - Ei[TL]) * dtdz;
+  }
+  {
+    const double* __restrict__ Ein = EMF + tile_off<3>(c + sj + 1);
+    const double* __restrict__ Ekn = EMF + tile_off<3>(c + sj + sk);
+    B1 -= (Ein[2 * TL] - Ej[2 * TL]) * dtdx;
+    B1 += (Ekn[0] - Ej[0]) * dtdz;
+  }
+  {
+    const double* __restrict__ Ein = EMF + tile_off<3>(c + sk + 1);
+    const double* __restrict__ Ejn = EMF + tile_off<3>(c + sk + sj);
+    C1 += (Ein[TL] - Ek[TL]) * dtdx;
+    C1 -= (Ejn[0] - Ek[0]) * dtdy;
+  }
+  un[IA] = A;
+  un[IB] = B;
+  un[IC] = C;
+  double q[8];
+  mhd_cons_to_prim(g, un, A1, B1, C1, q);
+  return mhd_cell_invdt(g, q);
+}
+
+EK_HD void mhd_stage_update(const Grid& g, const double* __restrict__ Uin, const double* __restrict__ F, const double* __restrict__ EMF,
+                            double* __restrict__ Uout, double dtdx, double dtdy, double dtdz, const MhdIdx& x)
+{
+  mhd_stage_update_t<false>(g, Uin, F, EMF, Uout, dtdx, dtdy, dtdz, x);
 }
 
 } // namespace ek

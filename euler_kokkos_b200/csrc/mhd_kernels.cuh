@@ -157,6 +157,25 @@ __global__ void __launch_bounds__(128, EK_MHD_R_MINB) mhd_faces_edges_kernel(con
   }
 }
 
+// block maximum of m (256-thread CTAs) into the running max of the inverse dt: warp shuffles, one atomic per CTA
+__device__ __forceinline__ void mhd_block_max_invdt(double m, TimeState* ts)
+{
+  __shared__ double red[8];
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0)
+    red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double r = (threadIdx.x < 8) ? red[threadIdx.x] : 0.0;
+    r = warp_max(r);
+    if (threadIdx.x == 0 && r > 0.0)
+      atomic_max_nonneg(&ts->invdt_bits, r);
+  }
+}
+
+// stage U.  INVDT: the CFL reduction of the NEXT step rides along (every interior cell except the last layer along
+// x, y, z, see mhd_stage_update_t); pre_step_kernel has zeroed ts->invdt_bits before the step's kernels run.
+template <bool INVDT>
 __global__ void __launch_bounds__(256) mhd_update_kernel(const MhdArgs a)
 {
   if (a.ts->finished)
@@ -164,8 +183,48 @@ __global__ void __launch_bounds__(256) mhd_update_kernel(const MhdArgs a)
   const MhdWork w = mhd_work_split(a.work, a.g.sv);
   const double dt = a.ts->dt;
   MhdIdx x;
+  double m = 0.0;
   if (mhd_cell_of_thread(a, x) && x.k >= a.upd_klo && x.k < a.upd_khi)
-    mhd_stage_update(a.g, a.Uin, w.F, w.EMF, a.Uout, dt / a.g.dx, dt / a.g.dy, dt / a.g.dz, x);
+    m = mhd_stage_update_t<INVDT>(a.g, a.Uin, w.F, w.EMF, a.Uout, dt / a.g.dx, dt / a.g.dy, dt / a.g.dz, x);
+  if constexpr (INVDT)
+    mhd_block_max_invdt(m, a.ts);
+}
+
+// CFL contribution of the interior cells whose upper faces are ghosts: the last interior layer along x, y and z
+// (after the boundary fill / halo exchange of the new state).  Thread t -> cell of layer x (ny*nz cells), then y
+// (nx*nz), then z (nx*ny); edge cells are visited more than once, which a maximum does not mind.
+__global__ void __launch_bounds__(256) mhd_invdt_layers_kernel(const MhdArgs a)
+{
+  if (a.ts->finished)
+    return;
+  const Grid& g = a.g;
+  const unsigned nx = (unsigned)g.nx, ny = (unsigned)g.ny, nz = (unsigned)g.nz;
+  const unsigned n0 = ny * nz, n1 = nx * nz, n2 = nx * ny;
+  unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  double m = 0.0;
+  if (t < n0 + n1 + n2) {
+    unsigned i, j, k;
+    if (t < n0) {
+      i = nx - 1; j = t % ny; k = t / ny;
+    } else if (t < n0 + n1) {
+      t -= n0;
+      i = t % nx; j = ny - 1; k = t / nx;
+    } else {
+      t -= n0 + n1;
+      i = t % nx; j = t / nx; k = nz - 1;
+    }
+    MhdIdx x;
+    x.i = (int)i + g.gw;
+    x.j = (int)j + g.gw;
+    x.k = (int)k + g.gw;
+    x.sj = (unsigned)g.isize;
+    x.sk = (unsigned)g.sk;
+    x.c = (unsigned)x.i + x.sj * (unsigned)x.j + x.sk * (unsigned)x.k;
+    double q[8];
+    mhd_prims_at(g, a.Uin, x, q);
+    m = mhd_cell_invdt(g, q);
+  }
+  mhd_block_max_invdt(m, a.ts);
 }
 
 // ---- MHD_Muscl_2D: same stages on the 2-D box (one thread per cell, flattened index) --------------

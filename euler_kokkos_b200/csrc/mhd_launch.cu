@@ -40,6 +40,21 @@ static bool use_pet(const Ctx& c)
   return pet != 0 && c.p.dim == 3;
 }
 
+// CFL reduction of the next step inside the update kernel (3-D); EK_MHD_DTFOLD=0 restores the stand-alone pass
+bool mhd_dt_folded(const Ctx& c)
+{
+  const int v = getenv("EK_MHD_DTFOLD") ? atoi(getenv("EK_MHD_DTFOLD")) : 1;
+  return v != 0 && c.p.dim == 3;
+}
+
+static void launch_update(const Ctx& c, dim3 grid, const MhdArgs& a)
+{
+  if (mhd_dt_folded(c))
+    mhd_update_kernel<true><<<grid, 256, 0, c.stream>>>(a);
+  else
+    mhd_update_kernel<false><<<grid, 256, 0, c.stream>>>(a);
+}
+
 static unsigned blocks(const Grid& g, int threads) { return (unsigned)((g.sv + threads - 1) / threads); }
 static unsigned blocks(const MhdArgs& a, int threads)
 {
@@ -59,6 +74,18 @@ cudaError_t launch_mhd_invdt(Ctx& c, const double* U)
   return cudaGetLastError();
 }
 
+// CFL contribution of the last interior layers of the (ghost-filled) level U, on top of what the update kernel that
+// produced U has accumulated in ts->invdt_bits
+cudaError_t launch_mhd_invdt_layers(Ctx& c, const double* U)
+{
+  const MhdArgs a = make_args(c, U, nullptr);
+  const Grid& g = c.g;
+  const unsigned n = (unsigned)g.ny * g.nz + (unsigned)g.nx * g.nz + (unsigned)g.nx * g.ny;
+  mhd_invdt_layers_kernel<<<(n + 255) / 256, 256, 0, c.stream>>>(a);
+  c.launches++;
+  return cudaGetLastError();
+}
+
 // stage U restricted to planes: the END planes (first and last gw interior planes, what the z neighbours need as
 // ghosts) as two small flat launches, or the MIDDLE planes with the regular launch order
 static void launch_update_ends(Ctx& c, MhdArgs a)
@@ -72,7 +99,7 @@ static void launch_update_ends(Ctx& c, MhdArgs a)
     a.upd_klo = k0[e];
     a.upd_khi = k0[e] + g.gw;
     const unsigned nthreads = per_plane * (unsigned)g.gw;
-    mhd_update_kernel<<<(nthreads + 255) / 256, 256, 0, c.stream>>>(a);
+    launch_update(c, dim3((nthreads + 255) / 256), a);
     c.launches++;
   }
 }
@@ -86,7 +113,7 @@ static cudaError_t launch_step(Ctx& c, const double* Uin, double* Uout, int part
     MhdArgs m = zgrouped(c, a, 256);
     m.upd_klo = 2 * c.g.gw;
     m.upd_khi = c.g.nz;
-    mhd_update_kernel<<<blocks(m, 256), 256, 0, c.stream>>>(m);
+    launch_update(c, dim3(blocks(m, 256)), m);
     c.launches++;
     return cudaGetLastError();
   }
@@ -161,7 +188,7 @@ static cudaError_t launch_step(Ctx& c, const double* Uin, double* Uout, int part
   if (part == 1) {
     launch_update_ends(c, a);
   } else {
-    mhd_update_kernel<<<blocks(a8, 256), 256, 0, c.stream>>>(a8);
+    launch_update(c, dim3(blocks(a8, 256)), a8);
     c.launches++;
   }
   return cudaGetLastError();

@@ -122,3 +122,40 @@ def test_mhd3d_kernel_variants_agree_with_the_oracle(knobs, monkeypatch):
     p = util.make_params(dim=3, mhd=True, n=(45, 26, 19), riemann="hlld", bc=(3, 3, 1, 2, 2, 1), smallr=1e-8, smallc=1e-8,
                          box=((0, 1.0), (0, 0.8), (0, 0.5)))
     _check_steps(p, util.random_hydro_state(p, seed=5, mach=2.5), 2)
+
+
+@pytest.mark.parametrize("bc", [(3, 3, 3, 3, 3, 3), (1, 1, 1, 1, 1, 1), (2, 2, 1, 3, 3, 2)])
+@pytest.mark.parametrize("layer", ["x", "y", "z", "corner", "none"])
+def test_mhd3d_folded_cfl_reduction_equals_the_standalone_pass(layer, bc, monkeypatch):
+    """The CFL maximum of the next step is reduced inside the update kernel for every interior cell but the last layer
+    along x, y, z (whose upper faces are ghosts) + a small kernel on those layers after the boundary fill.  With the
+    fastest cells placed IN those layers (or nowhere special) the device-resident time loop must use the same dt, and
+    end in the same state, as the stand-alone reduction over the ghost-filled state (ComputeDtFunctor3D_MHD)."""
+    from euler_kokkos_b200 import capi
+
+    p = util.make_params(dim=3, mhd=True, n=(22, 14, 11), riemann="hlld", bc=bc, smallr=1e-8, smallc=1e-8)
+    U0 = util.random_hydro_state(p, seed=3)
+    gw = p.ghost
+    sl = {"x": np.s_[:, :, :, gw + p.nx - 1], "y": np.s_[:, :, gw + p.ny - 1, :], "z": np.s_[:, gw + p.nz - 1, :, :],
+          "corner": np.s_[:, gw + p.nz - 1, gw + p.ny - 1, gw + p.nx - 1]}
+    if layer != "none":
+        fast = U0[sl[layer]]
+        fast[2:5] *= 6.0  # momenta: these cells now set the time step
+        fast[1] += 0.5 * (fast[2] ** 2 + fast[3] ** 2 + fast[4] ** 2) / fast[0]  # keep the pressure positive
+    out = {}
+    for fold in ("1", "0"):
+        monkeypatch.setenv("EK_MHD_DTFOLD", fold)
+        ctx = capi.Context(p)
+        ctx.upload(U0)
+        dts = []
+        for _ in range(3):  # three ek_run calls of one step: dt of steps 2 and 3 comes from the folded reduction
+            _, dt_last, n = ctx.run(1)
+            assert n == 1
+            dts.append(dt_last)
+        dt_next = ctx.compute_dt()  # host query on the level the last update produced
+        out[fold] = (dts, dt_next, ctx.download())
+        ctx.close()
+    for a, b in zip(out["1"][0] + [out["1"][1]], out["0"][0] + [out["0"][1]]):
+        assert abs(a - b) <= 1e-15 * abs(b), (out["1"][:2], out["0"][:2])
+    err = util.group_rel_linf(out["1"][2], out["0"][2], p)
+    assert max(err.values()) < 1e-14, err
