@@ -176,7 +176,7 @@ __device__ __forceinline__ void mhd_block_max_invdt(double m, TimeState* ts)
 // stage U.  INVDT: the CFL reduction of the NEXT step rides along (every interior cell except the last layer along
 // x, y, z, see mhd_stage_update_t); pre_step_kernel has zeroed ts->invdt_bits before the step's kernels run.
 template <bool INVDT>
-__global__ void __launch_bounds__(256) mhd_update_kernel(const MhdArgs a)
+__global__ void __launch_bounds__(256, 5) mhd_update_kernel(const MhdArgs a)
 {
   if (a.ts->finished)
     return;
