@@ -20,6 +20,10 @@ def lib():
         _lib.emul_mhd_work_len.restype = C.c_longlong
         _lib.emul_mhd_work_len.argtypes = [C.c_void_p]
         _lib.emul_mhd_step.argtypes = [C.c_void_p, dp, dp, dp, C.c_double]
+        _lib.emul_mhd_update_invdt.restype = C.c_double
+        _lib.emul_mhd_update_invdt.argtypes = [C.c_void_p, dp, dp, dp, C.c_double]
+        _lib.emul_mhd_invdt_layers.restype = C.c_double
+        _lib.emul_mhd_invdt_layers.argtypes = [C.c_void_p, dp]
         _lib.emul_chunk_map_check.restype = C.c_longlong
         _lib.emul_chunk_map_check.argtypes = [C.c_int] * 5
     return _lib
@@ -41,6 +45,21 @@ def mhd_step(p, U, dt):
     rc = lib().emul_mhd_step(C.byref(p), _dp(U), _dp(out), _dp(work), float(dt))
     assert rc == 0
     return out
+
+
+def mhd_step_with_partial_invdt(p, U, dt):
+    """3-D step through the update stage of mhd_update_kernel<true>: (new state, partial max of the next inverse dt)."""
+    work = np.zeros(lib().emul_mhd_work_len(C.byref(p)))
+    out = U.copy()
+    assert lib().emul_mhd_step(C.byref(p), _dp(U), _dp(out), _dp(work), float(dt)) == 0
+    out2 = U.copy()
+    partial = lib().emul_mhd_update_invdt(C.byref(p), _dp(U), _dp(out2), _dp(work), float(dt))
+    assert np.array_equal(out, out2)
+    return out, partial
+
+
+def mhd_invdt_layers(p, U):
+    return lib().emul_mhd_invdt_layers(C.byref(p), _dp(U))
 
 
 def chunk_map_violations(isize, jsize, ksize, yc, kg=1):

@@ -34,6 +34,17 @@ static void step(const Grid& g, const double* Uin, double* Uout, double* work, d
   LOOP mhd_stage_update(g, Uin, w.F, w.EMF, Uout, dtdx, dtdy, dtdz, x);
 }
 
+// the update stage as mhd_update_kernel<true> runs it: new state + the part of the next step's CFL maximum that can
+// be formed before the boundary fill (work must hold the fluxes and EMFs of a preceding step())
+static double update_with_invdt(const Grid& g, const double* Uin, double* Uout, double* work, double dt)
+{
+  const MhdWork w = mhd_work_split(work, g.sv);
+  const double dtdx = dt / g.dx, dtdy = dt / g.dy, dtdz = dt / g.dz;
+  double m = 0.0;
+  LOOP m = fmax(m, mhd_stage_update_t<true>(g, Uin, w.F, w.EMF, Uout, dtdx, dtdy, dtdz, x));
+  return m;
+}
+
 template <int RS>
 static void step2d(const Grid& g, const double* Uin, double* Uout, double* work, double dt)
 {
@@ -59,6 +70,32 @@ double emul_mhd_invdt(const ek_params* p, const double* U, double* work)
   }
   const MhdWork w = mhd_work_split(work, g.sv);
   LOOP m = fmax(m, mhd_stage_prims(g, U, w.Q, x));
+  return m;
+}
+
+// 3-D: the folded CFL reduction.  After emul_mhd_step (fluxes and EMFs still in `work`): redo the update stage the way
+// mhd_update_kernel<true> does and return its partial maximum ...
+double emul_mhd_update_invdt(const ek_params* p, const double* Uin, double* Uout, double* work, double dt)
+{
+  return update_with_invdt(make_grid(*p), Uin, Uout, work, dt);
+}
+
+// ... and the contribution of the last interior layer along x, y, z of a ghost-filled state (mhd_invdt_layers_kernel)
+double emul_mhd_invdt_layers(const ek_params* p, const double* U)
+{
+  const Grid g = make_grid(*p);
+  const int gw = g.gw;
+  double m = 0.0;
+  for (int k = gw; k < g.ksize - gw; ++k)
+    for (int j = gw; j < g.jsize - gw; ++j)
+      for (int i = gw; i < g.isize - gw; ++i) {
+        if (i != g.isize - gw - 1 && j != g.jsize - gw - 1 && k != g.ksize - gw - 1)
+          continue;
+        const MhdIdx x = idx(g, i, j, k);
+        double q[8];
+        mhd_prims_at(g, U, x, q);
+        m = fmax(m, mhd_cell_invdt(g, q));
+      }
   return m;
 }
 

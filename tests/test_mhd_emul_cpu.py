@@ -71,3 +71,36 @@ def test_chunked_launch_order_covers_every_cell_once(shape, yc, kg):
     from tests.emul import emul_lib as E
 
     assert E.chunk_map_violations(*shape, yc, kg) == 0
+
+
+@pytest.mark.parametrize("bc", [(3, 3, 3, 3, 3, 3), (1, 1, 2, 2, 1, 2)])
+@pytest.mark.parametrize("layer", ["x", "y", "z", "corner", "none"])
+def test_emul_folded_cfl_reduction(layer, bc):
+    """mhd_update_kernel<true> + mhd_invdt_layers_kernel (host build of the same per-cell code): the partial maximum
+    formed inside the update plus the last-layer pass after the boundary fill equals the stand-alone reduction over
+    the ghost-filled new state bit for bit, and the oracle's (ComputeDtFunctor3D_MHD) to round-off -- also when the
+    fastest cells sit in the layers whose upper faces are ghosts."""
+    from oracle import oracle_lib as O
+    from tests.emul import emul_lib as E
+
+    p = util.make_params(dim=3, mhd=True, n=(12, 10, 9), riemann="hlld", bc=bc, smallr=1e-8, smallc=1e-8)
+    U = util.random_hydro_state(p, seed=4)
+    gw = p.ghost
+    sl = {"x": np.s_[:, :, :, gw + p.nx - 1], "y": np.s_[:, :, gw + p.ny - 1, :], "z": np.s_[:, gw + p.nz - 1, :, :],
+          "corner": np.s_[:, gw + p.nz - 1, gw + p.ny - 1, gw + p.nx - 1]}
+    if layer != "none":
+        fast = U[sl[layer]]
+        fast[2:5] *= 6.0
+        fast[1] += 0.5 * (fast[2] ** 2 + fast[3] ** 2 + fast[4] ** 2) / fast[0]
+    op = O.params_from(p)
+    O.make_boundaries(op, U)
+    dt = op.cfl / O.invdt(op, U)
+    U1, partial = E.mhd_step_with_partial_invdt(p, U, dt)
+    O.make_boundaries(op, U1)
+    layers = E.mhd_invdt_layers(p, U1)
+    full = E.mhd_invdt(p, U1)
+    assert max(partial, layers) == full, (partial, layers, full)
+    if layer != "none":
+        assert layers >= partial  # the fast cells are where only the layer pass can see them
+    inv_o = O.invdt(op, U1)
+    assert abs(full - inv_o) <= 1e-13 * inv_o
