@@ -19,6 +19,7 @@ struct MhdArgs {
   MhdChunkMap cm; // thread -> cell order of the 3-D stencil stages (yc = 0: flat)
   unsigned t0 = 0; // offset added to the linear thread index (flat order: launches restricted to a range of planes)
   int upd_klo = 0, upd_khi = 1 << 30; // planes [upd_klo, upd_khi) the update kernel may write
+  int r_pf = 0; // stage R: L2 prefetch of the compact state this many planes ahead (0 = off)
 };
 
 __device__ __forceinline__ bool mhd_cell_of_thread(const MhdArgs& a, MhdIdx& x)

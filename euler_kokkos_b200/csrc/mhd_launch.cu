@@ -168,7 +168,11 @@ static cudaError_t launch_step(Ctx& c, const double* Uin, double* Uout, int part
   // 0 = fully inlined (mhd_staged.cuh has the measurements)
   const int staged = getenv("EK_MHD_STAGED") ? atoi(getenv("EK_MHD_STAGED")) : 2;
   if (staged == 2) {
-    mhd_faces_edges_call_kernel<RS><<<blocks(a4, 128), 128, 0, c.stream>>>(a4);
+    MhdArgs ar = a4;
+    ar.r_pf = getenv("EK_MHD_R_PF") ? atoi(getenv("EK_MHD_R_PF")) : 0; // planes ahead (y-chunked order only)
+    if (!ar.cm.yc)
+      ar.r_pf = 0;
+    mhd_faces_edges_call_kernel<RS><<<blocks(ar, 128), 128, 0, c.stream>>>(ar);
     c.launches++;
   } else if (staged) {
     static bool attr_done[16] = { false };

@@ -330,6 +330,14 @@ __global__ void __launch_bounds__(128, 4) mhd_faces_edges_call_kernel(const MhdA
   const double* __restrict__ S001 = S + tile_off<S_TOTAL>(c - sk);
   double* __restrict__ Fc = w.F + tile_off<15>(c);
   double* __restrict__ Ec = w.EMF + tile_off<3>(c);
+  if (a.r_pf > 0 && x.k + a.r_pf <= g.ksize - g.gw) {
+    // the same column a.r_pf planes ahead is taken by a later wave of this y-slab: have its compact state brought
+    // from DRAM to L2 now (each S row is touched for the first time by the thread that owns it)
+    const double* __restrict__ Sn = S + tile_off<S_TOTAL>(c + (unsigned)a.r_pf * sk);
+#pragma unroll
+    for (int v = 0; v < S_TOTAL; ++v)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(Sn + TL * v));
+  }
   call_face<0, RS>(g, S100, S000, Fc);
   call_face<1, RS>(g, S010, S000, Fc);
   call_face<2, RS>(g, S001, S000, Fc);
