@@ -119,15 +119,12 @@ static cudaError_t launch_step(Ctx& c, const double* Uin, double* Uout, int part
   }
   const MhdArgs a8 = zgrouped(c, a, 256), a4 = zgrouped(c, a, 128);
   if (use_pet(c)) {
-    // EK_MHD_PET_EARLY=1: the variant that requests the next plane's conserved state before the predictor
-    const int early = getenv("EK_MHD_PET_EARLY") ? (atoi(getenv("EK_MHD_PET_EARLY")) != 0) : 0;
-    void (*pet)(const MhdArgs, const int, const int) = early ? mhd_pet_kernel<1> : mhd_pet_kernel<0>;
-    static bool pet_attr[16][2] = { { false } };
-    if (!pet_attr[c.device & 15][early]) {
-      cudaError_t e = cudaFuncSetAttribute(pet, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PetSmem));
+    static bool pet_attr[16] = { false };
+    if (!pet_attr[c.device & 15]) {
+      cudaError_t e = cudaFuncSetAttribute(mhd_pet_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PetSmem));
       if (e != cudaSuccess)
         return e;
-      pet_attr[c.device & 15][early] = true;
+      pet_attr[c.device & 15] = true;
     }
     const Grid& g = c.g;
     dim3 grid((g.isize - 3 + PET_TX - 1) / PET_TX, (g.jsize - 3 + PET_TY - 1) / PET_TY, 1); // cells 2 .. isize-2
@@ -150,7 +147,7 @@ static cudaError_t launch_step(Ctx& c, const double* Uin, double* Uout, int part
     const int zchunk = (nplanes + nchunk - 1) / nchunk;
     grid.z = (nplanes + zchunk - 1) / zchunk;
     static const int pet_pf = getenv("EK_MHD_PET_PF") ? atoi(getenv("EK_MHD_PET_PF")) : 0; // L2 prefetch of the plane converted next
-    pet<<<grid, PET_TX * PET_TY, sizeof(PetSmem), c.stream>>>(a, zchunk, pet_pf);
+    mhd_pet_kernel<0><<<grid, PET_TX * PET_TY, sizeof(PetSmem), c.stream>>>(a, zchunk, pet_pf);
     c.launches++;
     c.mhd_prims_of = nullptr;
   } else {

@@ -23,8 +23,7 @@ struct PetSmem {
   double e[2][PET_EPLANE];
 };
 
-// EARLY = 1: pass A of the next conversion is requested before the predictor (see the main loop)
-template <int EARLY = 0>
+template <int DUMMY = 0>
 __global__ void __launch_bounds__(PET_TX* PET_TY, 2) mhd_pet_kernel(const MhdArgs a, const int zchunk, const int l2_prefetch)
 {
   extern __shared__ __align__(16) unsigned char pet_raw[];
@@ -60,31 +59,34 @@ __global__ void __launch_bounds__(PET_TX* PET_TY, 2) mhd_pet_kernel(const MhdArg
 
   // primitives of the box cells of plane k -> ring slot k & 3 (cells the reference never converts are skipped);
   // the loads of both passes are issued before the first conversion
-  // split in three so that the main loop can request pass A BEFORE the predictor of the current plane (the 11 values
-  // ride through it in registers: the predictor needs ~80 of the 128 available) and convert right after it
-  auto prims_load = [&](int k, int b, bool has, double* __restrict__ u) {
-    MhdIdx x;
-    cell_of_box(has ? b : bA, k, x);
-    const bool ok = has && k < g.ksize - 1 && x.i < g.isize - 1 && x.j < g.jsize - 1;
-    mhd_cons_load(g, a.Uin, x, ok, u);
-    return ok;
-  };
-  auto prims_store = [&](int k, int b, bool ok, const double* __restrict__ u) {
-    if (!ok)
-      return;
-    double q[8];
-    mhd_cons_to_prim(g, u, u[8], u[9], u[10], q);
-    double* __restrict__ qc = sm.q[k & 3] + tile_off<8>((unsigned)b);
-#pragma unroll
-    for (int v = 0; v < 8; ++v)
-      qc[TL * v] = q[v];
-  };
   auto prims_plane = [&](int k) {
+    if (k >= g.ksize - 1)
+      return;
+    double* __restrict__ qs = sm.q[k & 3];
+    MhdIdx xA, xB;
+    cell_of_box(bA, k, xA);
+    cell_of_box(hasB ? bB : bA, k, xB);
+    const bool okA = xA.i < g.isize - 1 && xA.j < g.jsize - 1;
+    const bool okB = hasB && xB.i < g.isize - 1 && xB.j < g.jsize - 1;
     double uA[11], uB[11];
-    const bool okA = prims_load(k, bA, true, uA);
-    const bool okB = prims_load(k, bB, hasB, uB);
-    prims_store(k, bA, okA, uA);
-    prims_store(k, bB, okB, uB);
+    mhd_cons_load(g, a.Uin, xA, okA, uA);
+    mhd_cons_load(g, a.Uin, xB, okB, uB);
+    if (okA) {
+      double q[8];
+      mhd_cons_to_prim(g, uA, uA[8], uA[9], uA[10], q);
+      double* __restrict__ qc = qs + tile_off<8>((unsigned)bA);
+#pragma unroll
+      for (int v = 0; v < 8; ++v)
+        qc[TL * v] = q[v];
+    }
+    if (okB) {
+      double q[8];
+      mhd_cons_to_prim(g, uB, uB[8], uB[9], uB[10], q);
+      double* __restrict__ qc = qs + tile_off<8>((unsigned)bB);
+#pragma unroll
+      for (int v = 0; v < 8; ++v)
+        qc[TL * v] = q[v];
+    }
   };
   // edge field of plane k (needs the primitives of planes k-1 and k) -> slot k & 1.  The face-centred field values
   // come from the conserved state: elec_load issues those loads (before the barrier that publishes the primitives),
@@ -149,12 +151,6 @@ __global__ void __launch_bounds__(PET_TX* PET_TY, 2) mhd_pet_kernel(const MhdArg
   __syncthreads();
 
   for (int p = kbeg; p < kend; ++p) {
-    // pass A of the conversion of plane p+2: loads requested now, consumed after the predictor of plane p
-    double uA[11];
-    const bool more = p + 1 < kend;
-    bool okA = false;
-    if constexpr (EARLY != 0)
-      okA = more && prims_load(p + 2, bA, true, uA);
     if (l2_prefetch && p + 3 < g.ksize - 1) {
       // the conserved state this thread converts next iteration: ask L2 for it now (first touch comes from DRAM)
       MhdIdx x;
@@ -193,21 +189,14 @@ __global__ void __launch_bounds__(PET_TX* PET_TY, 2) mhd_pet_kernel(const MhdArg
         mhd_trace_core(g, fb, P, w.S + tile_off<S_TOTAL>(x.c), dtdx, dtdy, dtdz, x);
       }
     }
-    if (more) {
+    if (p + 1 < kend) {
       // the next plane's field values are requested now and consumed after the two barriers below
       {
         MhdIdx x;
         const bool act = trace_cell(p + 1, x);
         mhd_trace_load(g, a.Uin, x, act, fb);
       }
-      {
-        double uB[11];
-        if constexpr (EARLY == 0)
-          okA = prims_load(p + 2, bA, true, uA);
-        const bool okB = prims_load(p + 2, bB, hasB, uB);
-        prims_store(p + 2, bA, okA, uA); // slot (p+2)&3 held plane p-2: free
-        prims_store(p + 2, bB, okB, uB);
-      }
+      prims_plane(p + 2); // slot (p+2)&3 held plane p-2: free
       elec_load(p + 2, eA, eB);
       __syncthreads();
       elec_plane(p + 2, eA, eB); // slot p&1 held plane p: its readers passed the barrier above

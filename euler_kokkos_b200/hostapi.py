@@ -134,7 +134,10 @@ class Case:
         return f"{name}, riemann={rs}, impl={p.impl_version}, problem={self.get_string('hydro', 'problem')}"
 
     def kernel_name(self) -> str:
-        return "mhd_step (staged kernels)" if self.params.mhd else f"hydro_step_kernel<{self.params.dim}>"
+        if self.params.mhd:
+            return ("mhd step kernels (mhd_pet + mhd_faces_edges_call + mhd_update)" if self.params.dim == 3
+                    else "mhd2d step kernels (prims + elec + trace + faces_edge + update)")
+        return f"hydro_step_kernel<{self.params.dim}>"
 
 
 def write_ini(src_ini: str, overrides, dst_path: str):
