@@ -17,14 +17,16 @@ struct MhdArgs {
   double* __restrict__ work;
   TimeState* ts;
   MhdChunkMap cm; // thread -> cell order of the 3-D stencil stages (yc = 0: flat)
-  unsigned t0 = 0; // offset added to the linear thread index (flat order: launches restricted to a range of planes)
+  unsigned t0 = 0; // offset added to the linear thread index (launches restricted to a range of planes / of y-slabs)
+  unsigned t1 = 0xffffffffu; // one past the last linear thread index this launch may take
   int upd_klo = 0, upd_khi = 1 << 30; // planes [upd_klo, upd_khi) the update kernel may write
   int r_pf = 0; // stage R: L2 prefetch of the compact state this many planes ahead (0 = off)
 };
 
 __device__ __forceinline__ bool mhd_cell_of_thread(const MhdArgs& a, MhdIdx& x)
 {
-  return mhd_chunk_cell(a.g, a.cm, a.t0 + blockIdx.x * blockDim.x + threadIdx.x, x);
+  const unsigned t = a.t0 + blockIdx.x * blockDim.x + threadIdx.x;
+  return t < a.t1 && mhd_chunk_cell(a.g, a.cm, t, x);
 }
 
 __device__ __forceinline__ bool mhd_cell_of_thread(const Grid& g, MhdIdx& x)

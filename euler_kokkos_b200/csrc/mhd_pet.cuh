@@ -24,7 +24,7 @@ struct PetSmem {
 };
 
 template <int DUMMY = 0>
-__global__ void __launch_bounds__(PET_TX* PET_TY, 2) mhd_pet_kernel(const MhdArgs a, const int zchunk, const int l2_prefetch)
+__global__ void __launch_bounds__(PET_TX* PET_TY, 2) mhd_pet_kernel(const MhdArgs a, const int zchunk, const int l2_prefetch, const int ty0 = 0)
 {
   extern __shared__ __align__(16) unsigned char pet_raw[];
   PetSmem& sm = *reinterpret_cast<PetSmem*>(pet_raw);
@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(PET_TX* PET_TY, 2) mhd_pet_kernel(const MhdArg
   const double dt = a.ts->dt;
   const double dtdx = dt / g.dx, dtdy = dt / g.dy, dtdz = dt / g.dz;
   const int t = threadIdx.x;
-  const int i0 = 2 + PET_TX * blockIdx.x, j0 = 2 + PET_TY * blockIdx.y; // first cell of the tile (ghosted coordinates)
+  const int i0 = 2 + PET_TX * blockIdx.x, j0 = 2 + PET_TY * ((int)blockIdx.y + ty0); // ty0: first tile row of this launch // first cell of the tile (ghosted coordinates)
   const int kbeg = 2 + (int)blockIdx.z * zchunk;
   const int kend = min(kbeg + zchunk, g.ksize - 1); // the predictor runs on planes 2 .. ksize-2
   if (kbeg >= kend)
