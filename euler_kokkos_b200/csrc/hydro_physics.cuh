@@ -19,7 +19,7 @@ struct HydroTraits {
 
 // ---- conservative -> primitive ---------------------------------------------------------------
 template <int DIM>
-__device__ __forceinline__ void hydro_cons_to_prim(const Grid& g, const double* __restrict__ u, double* __restrict__ q,
+EK_HD void hydro_cons_to_prim(const Grid& g, const double* __restrict__ u, double* __restrict__ q,
                                                    double& rd_out)
 {
   const double d = dmax(u[ID], g.smallr);
@@ -45,7 +45,7 @@ __device__ __forceinline__ void hydro_cons_to_prim(const Grid& g, const double* 
 // inverse-dt contribution of one cell (ComputeDtFunctor{2D,3D}, HydroRunFunctors3D.h:44-82;
 // ComputeDtGravityFunctor{2D,3D}, :133-189)
 template <int DIM, bool GRAV>
-__device__ __forceinline__ double hydro_cell_invdt(const Grid& g, const double* __restrict__ u, const double* __restrict__ gvec)
+EK_HD double hydro_cell_invdt(const Grid& g, const double* __restrict__ u, const double* __restrict__ gvec)
 {
   double q[5], rd;
   hydro_cons_to_prim<DIM>(g, u, q, rd);
@@ -73,7 +73,7 @@ __device__ __forceinline__ double hydro_cell_invdt(const Grid& g, const double* 
 }
 
 // ---- limited slope ---------------------------------------------------------------------------
-__device__ __forceinline__ double limited_slope(double st, double sk, double qm, double q, double qp)
+EK_HD double limited_slope(double st, double sk, double qm, double q, double qp)
 {
   return limited_slope_ref(st, sk, qm, q, qp);
 }
@@ -81,7 +81,7 @@ __device__ __forceinline__ double limited_slope(double st, double sk, double qm,
 // ---- Hancock predictor: source terms of one cell ---------------------------------------------
 // s[v] = time derivative of primitive variable v (to be multiplied by dt/dx_d * 0.5 per face)
 template <int DIM>
-__device__ __forceinline__ void hydro_sources(const Grid& g, const double* __restrict__ q, const double (*dq)[5], double* __restrict__ s)
+EK_HD void hydro_sources(const Grid& g, const double* __restrict__ q, const double (*dq)[5], double* __restrict__ s)
 {
   const double r = q[ID], p = q[IP], u = q[IU], v = q[IV];
   const double rr = rcp_fast(r);
@@ -104,7 +104,7 @@ __device__ __forceinline__ void hydro_sources(const Grid& g, const double* __res
 
 // ---- Riemann solvers: q = (rho, p, un, ut1[, ut2]) in the face-normal frame -------------------
 template <int DIM>
-__device__ __forceinline__ void riemann_hllc(const Grid& g, const double* __restrict__ ql, const double* __restrict__ qr, double* __restrict__ flux)
+EK_HD void riemann_hllc(const Grid& g, const double* __restrict__ ql, const double* __restrict__ qr, double* __restrict__ flux)
 {
   const double entho = g.entho;
   const double rl = dmax(ql[ID], g.smallr);
@@ -169,7 +169,7 @@ __device__ __forceinline__ void riemann_hllc(const Grid& g, const double* __rest
 }
 
 template <int DIM>
-__device__ __forceinline__ void hydro_cmpflx(const Grid& g, const double* __restrict__ qg, double* __restrict__ flux)
+EK_HD void hydro_cmpflx(const Grid& g, const double* __restrict__ qg, double* __restrict__ flux)
 {
   const double fm = qg[ID] * qg[IU];
   flux[ID] = fm;
@@ -195,7 +195,7 @@ __device__ __forceinline__ void hydro_cmpflx(const Grid& g, const double* __rest
 //   * a problem that has converged keeps its state (select), exactly like leaving the reference's loop.
 // Per iteration and problem about 50 FP64-pipe instructions instead of about 280 with IEEE '/' and sqrt().
 template <int DIM, int N>
-__device__ __forceinline__ void riemann_approx_n(const Grid& g, const double (*ql)[5], const double (*qr)[5], double (*flux)[5])
+EK_HD void riemann_approx_n(const Grid& g, const double (*ql)[5], const double (*qr)[5], double (*flux)[5])
 {
   const double gamma0 = g.gamma0, gamma6 = g.gamma6;
   double rl[N], ul[N], pl[N], rr[N], ur[N], pr[N], cl[N], cr[N], ipl[N], ipr[N], pold[N];
@@ -283,7 +283,7 @@ __device__ __forceinline__ void riemann_approx_n(const Grid& g, const double (*q
 }
 
 template <int DIM>
-__device__ __forceinline__ void riemann_approx(const Grid& g, const double* __restrict__ ql, const double* __restrict__ qr, double* __restrict__ flux)
+EK_HD void riemann_approx(const Grid& g, const double* __restrict__ ql, const double* __restrict__ qr, double* __restrict__ flux)
 {
   double l[1][5], r[1][5], f[1][5];
 #pragma unroll
@@ -299,7 +299,7 @@ __device__ __forceinline__ void riemann_approx(const Grid& g, const double* __re
 
 // conservative state + physical flux of one side (LLF / HLL)
 template <int DIM, bool HLL>
-__device__ __forceinline__ void hydro_cons_flux(const double* __restrict__ q, double entho, double* __restrict__ u, double* __restrict__ f)
+EK_HD void hydro_cons_flux(const double* __restrict__ q, double entho, double* __restrict__ u, double* __restrict__ f)
 {
   u[ID] = q[ID];
   double e = q[IP] * entho + 0.5 * q[ID] * q[IU] * q[IU];
@@ -320,7 +320,7 @@ __device__ __forceinline__ void hydro_cons_flux(const double* __restrict__ q, do
 }
 
 template <int DIM>
-__device__ __forceinline__ void riemann_llf(const Grid& g, const double* __restrict__ ql, const double* __restrict__ qr, double* __restrict__ flux)
+EK_HD void riemann_llf(const Grid& g, const double* __restrict__ ql, const double* __restrict__ qr, double* __restrict__ flux)
 {
   constexpr int NV = HydroTraits<DIM>::NV;
   const double entho = g.entho;
@@ -338,7 +338,7 @@ __device__ __forceinline__ void riemann_llf(const Grid& g, const double* __restr
 }
 
 template <int DIM>
-__device__ __forceinline__ void riemann_hll(const Grid& g, const double* __restrict__ ql, const double* __restrict__ qr, double* __restrict__ flux)
+EK_HD void riemann_hll(const Grid& g, const double* __restrict__ ql, const double* __restrict__ qr, double* __restrict__ flux)
 {
   constexpr int NV = HydroTraits<DIM>::NV;
   const double entho = g.entho;
@@ -358,7 +358,7 @@ __device__ __forceinline__ void riemann_hll(const Grid& g, const double* __restr
 }
 
 template <int DIM, int RS>
-__device__ __forceinline__ void riemann_hydro(const Grid& g, const double* __restrict__ ql, const double* __restrict__ qr, double* __restrict__ flux)
+EK_HD void riemann_hydro(const Grid& g, const double* __restrict__ ql, const double* __restrict__ qr, double* __restrict__ flux)
 {
   if constexpr (RS == RIEMANN_HLLC)
     riemann_hllc<DIM>(g, ql, qr, flux);
@@ -374,7 +374,7 @@ __device__ __forceinline__ void riemann_hydro(const Grid& g, const double* __res
 // dependency chains of the N faces interleave: the solver is a long serial chain (two reciprocal
 // Newton sequences and a square root), and a CTA only has 4 warps per scheduler to hide it.
 template <int DIM, int N>
-__device__ __forceinline__ void riemann_hllc_n(const Grid& g, const double (*ql)[5], const double (*qr)[5], double (*flux)[5])
+EK_HD void riemann_hllc_n(const Grid& g, const double (*ql)[5], const double (*qr)[5], double (*flux)[5])
 {
   const double entho = g.entho;
   const double sc2 = g.smallc * g.smallc;
@@ -466,7 +466,7 @@ __device__ __forceinline__ void riemann_hllc_n(const Grid& g, const double (*ql)
 }
 
 template <int DIM, int RS, int N>
-__device__ __forceinline__ void riemann_hydro_n(const Grid& g, const double (*ql)[5], const double (*qr)[5], double (*flux)[5])
+EK_HD void riemann_hydro_n(const Grid& g, const double (*ql)[5], const double (*qr)[5], double (*flux)[5])
 {
   if constexpr (RS == RIEMANN_HLLC) {
     riemann_hllc_n<DIM, N>(g, ql, qr, flux);

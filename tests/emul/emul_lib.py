@@ -24,6 +24,9 @@ def lib():
         _lib.emul_mhd_update_invdt.argtypes = [C.c_void_p, dp, dp, dp, C.c_double]
         _lib.emul_mhd_invdt_layers.restype = C.c_double
         _lib.emul_mhd_invdt_layers.argtypes = [C.c_void_p, dp]
+        _lib.emul_hydro_step.argtypes = [C.c_void_p, dp, dp, dp, C.c_double]
+        _lib.emul_hydro_invdt.restype = C.c_double
+        _lib.emul_hydro_invdt.argtypes = [C.c_void_p, dp, dp]
         _lib.emul_chunk_map_check.restype = C.c_longlong
         _lib.emul_chunk_map_check.argtypes = [C.c_int] * 5
     return _lib
@@ -64,3 +67,18 @@ def mhd_invdt_layers(p, U):
 
 def chunk_map_violations(isize, jsize, ksize, yc, kg=1):
     return lib().emul_chunk_map_check(isize, jsize, ksize, yc, kg)
+
+
+def hydro_step(p, U, dt, grav=None):
+    """U: ghost-filled state.  Returns the new state (ghosts copied from U) computed by the host build of the
+    per-cell functions of hydro_step_kernel, in the kernel's order of operations."""
+    out = U.copy()
+    g = _dp(grav) if grav is not None else None
+    rc = lib().emul_hydro_step(C.byref(p), _dp(U), _dp(out), g, float(dt))
+    assert rc == 0
+    return out
+
+
+def hydro_invdt(p, U, grav=None):
+    g = _dp(grav) if grav is not None else None
+    return lib().emul_hydro_invdt(C.byref(p), _dp(U), g)
