@@ -20,17 +20,22 @@ constexpr int TY = EK_HYDRO_TY;
 #define EK_HYDRO_TYF 14
 #endif
 constexpr int TYF = EK_HYDRO_TYF;
+// EK_HYDRO_FOLD=2 (experimental, not yet measured on a GPU): folded rows with 15 warps = 480 threads, 14 of them
+// solving, spread 4/4/3/3 over the schedulers
+constexpr int TYF2 = 13;
 
 // 3-D tile layout: 1 = folded halo rows, 28 x 14 tile, 16 warps; 0 = one warp per tile row incl. halo rows, 28 x 11,
 // 15 warps.  Measured at 512^3 (profiles/r01_hydro_fold_ncu.txt): the folded layout executes 3.4 % fewer
-// instructions and halves the barrier stalls, but its 512 threads leave 128 registers per thread instead of 136, the
-// three lock-step HLLC problems interleave less (fixed-latency "wait" stalls 0.98 -> 1.93 per issue) and it ends 1.6 %
+// instructions and halves the barrier stalls, but the three lock-step HLLC problems come out less interleaved (128
+// registers used instead of 122; fixed-latency "wait" stalls 0.98 -> 1.93 per issue) and it ends 1.6 %
 // slower (10.90 vs 10.73 ms); with the iterative two-shock solver + gravity it is 8 % faster (34.5 vs 37.5 ms).
 // Default: folded for riemann = approx, unfolded otherwise; EK_HYDRO_FOLD=0/1 forces one.
-static bool use_fold(int riemann)
+static int fold_rows(int riemann)
 {
   const int v = getenv("EK_HYDRO_FOLD") ? atoi(getenv("EK_HYDRO_FOLD")) : -1;
-  return v < 0 ? riemann == RIEMANN_APPROX : v != 0;
+  if (v < 0)
+    return riemann == RIEMANN_APPROX ? TYF : 0;
+  return v == 0 ? 0 : (v == 2 ? TYF2 : TYF);
 }
 
 // 3-D schedule: 0 (default) = two block barriers per plane (hydro_kernels.cuh); 1 = the one-barrier software
@@ -92,7 +97,7 @@ static ZPlan z_plan(const Ctx& c, long long xy_ctas, bool want_split)
   return z;
 }
 
-static int tile_rows(int dim, int riemann) { return (dim == 3 && use_fold(riemann) && !use_1b()) ? TYF : TY; }
+static int tile_rows(int dim, int riemann) { return (dim == 3 && fold_rows(riemann) > 0 && !use_1b()) ? fold_rows(riemann) : TY; }
 static long long hydro_xy_ctas(const Grid& g, int riemann)
 {
   const int ty = tile_rows(g.nz > 1 ? 3 : 2, riemann);
@@ -116,15 +121,21 @@ static cudaError_t launch_one(Ctx& c, const double* Uin, double* Uout, int part,
   }
   int ty = TY, warps = TY + 4;
   if constexpr (DIM == 3) {
-    if (tile_rows(3, RS) == TYF) {
+    const int tr = tile_rows(3, RS);
+    if (tr == TYF) {
       kern = hydro_step_kernel<DIM, RS, TYF, GRAV, 1>;
       smem = sizeof(HydroSmem<DIM, TYF>);
       ty = TYF;
       warps = TYF + 2;
+    } else if (tr == TYF2) {
+      kern = hydro_step_kernel<DIM, RS, TYF2, GRAV, 1>;
+      smem = sizeof(HydroSmem<DIM, TYF2>);
+      ty = TYF2;
+      warps = TYF2 + 2;
     }
   }
-  const int variant = (ty == TYF && DIM == 3) ? 2 : (use_1b() ? 1 : 0);
-  static bool attr_done[16][3] = { { false } };
+  const int variant = (DIM == 3 && ty == TYF) ? 2 : (DIM == 3 && ty == TYF2) ? 3 : (use_1b() ? 1 : 0);
+  static bool attr_done[16][4] = { { false } };
   if (!attr_done[c.device & 15][variant]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess)

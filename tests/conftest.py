@@ -10,6 +10,17 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "experimental: variants compiled but not yet run on a GPU; skipped unless "
+                            "EK_TEST_EXPERIMENTAL=1")
+
+
+def pytest_collection_modifyitems(config, items):
+    if os.environ.get("EK_TEST_EXPERIMENTAL") == "1":
+        return
+    skip = pytest.mark.skip(reason="experimental variant: set EK_TEST_EXPERIMENTAL=1")
+    for item in items:
+        if "experimental" in item.keywords:
+            item.add_marker(skip)
 
 
 @pytest.fixture(scope="session", autouse=True)

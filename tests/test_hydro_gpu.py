@@ -51,6 +51,15 @@ def test_hydro3d_kernel_variants_agree_with_the_oracle(knobs, riemann, monkeypat
     _check_steps(p, util.random_hydro_state(p, seed=11), 2)
 
 
+@pytest.mark.experimental
+@pytest.mark.parametrize("riemann", ["hllc", "approx", "llf"])
+def test_hydro3d_experimental_variants(riemann, monkeypatch):
+    """variants that compile but have not run on a GPU yet (EK_TEST_EXPERIMENTAL=1): folded rows with 15 warps."""
+    monkeypatch.setenv("EK_HYDRO_FOLD", "2")
+    p = util.make_params(dim=3, n=(61, 33, 40), riemann=riemann, bc=(3, 3, 1, 2, 2, 1))
+    _check_steps(p, util.random_hydro_state(p, seed=11), 2)
+
+
 @pytest.mark.parametrize("bc", [(1, 1, 1, 1, 1, 1), (2, 2, 2, 2, 2, 2), (3, 3, 3, 3, 3, 3), (3, 3, 1, 2, 2, 1)])
 def test_hydro3d_boundaries(bc):
     p = util.make_params(dim=3, n=(20, 14, 10), bc=bc)
