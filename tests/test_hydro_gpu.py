@@ -40,22 +40,13 @@ def test_hydro3d_one_step_parity(riemann, n):
     _check_steps(p, util.random_hydro_state(p, seed=1), 3)
 
 
-@pytest.mark.parametrize("knobs", [{"EK_HYDRO_FOLD": "0"}, {"EK_HYDRO_FOLD": "1"}, {"EK_HYDRO_1B": "1"}])
+@pytest.mark.parametrize("knobs", [{"EK_HYDRO_FOLD": "0"}, {"EK_HYDRO_FOLD": "1"}, {"EK_HYDRO_FOLD": "2"}, {"EK_HYDRO_1B": "1"}])
 @pytest.mark.parametrize("riemann", ["hllc", "approx", "llf"])
 def test_hydro3d_kernel_variants_agree_with_the_oracle(knobs, riemann, monkeypatch):
-    """every selectable 3-D schedule (one warp per tile row, folded halo rows, one barrier per plane) is held to the
+    """every selectable 3-D schedule (one warp per tile row, folded halo rows with 16 / 15 warps, one barrier per plane) is held to the
     same one-step tolerance, with reflective / outflow / periodic faces and several z chunks."""
     for k, v in knobs.items():
         monkeypatch.setenv(k, v)
-    p = util.make_params(dim=3, n=(61, 33, 40), riemann=riemann, bc=(3, 3, 1, 2, 2, 1))
-    _check_steps(p, util.random_hydro_state(p, seed=11), 2)
-
-
-@pytest.mark.experimental
-@pytest.mark.parametrize("riemann", ["hllc", "approx", "llf"])
-def test_hydro3d_experimental_variants(riemann, monkeypatch):
-    """variants that compile but have not run on a GPU yet (EK_TEST_EXPERIMENTAL=1): folded rows with 15 warps."""
-    monkeypatch.setenv("EK_HYDRO_FOLD", "2")
     p = util.make_params(dim=3, n=(61, 33, 40), riemann=riemann, bc=(3, 3, 1, 2, 2, 1))
     _check_steps(p, util.random_hydro_state(p, seed=11), 2)
 
