@@ -48,6 +48,34 @@ struct Grid {
 EK_HD double dmax(double a, double b) { return (a > b) ? a : b; }
 EK_HD double dmin(double a, double b) { return (a < b) ? a : b; }
 
+// max(a, 0) / min(a, 0).  With a literal 0.0 the compiler proves one operand non-NaN, turns the compare+select above
+// back into max.f64 / min.f64 and ptxas expands that to the NaN-aware sequence again (DSETP.MAX + FSEL + SEL +
+// predicated LOP3 + moves: 38 of them per thread in MHD stage R, cuobjdump).  The comparison is therefore written in
+// PTX: setp + selp = one DSETP and two FSEL.  Same result for every non-NaN a (and 0 for a NaN, as before).
+#ifndef EK_ASM_MAX0
+#define EK_ASM_MAX0 1
+#endif
+EK_HD double dmax0(double a)
+{
+#if EK_ASM_MAX0 && defined(__CUDA_ARCH__)
+  double r;
+  asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %1, 0d0000000000000000;\n\tselp.f64 %0, %1, 0d0000000000000000, p;\n\t}" : "=d"(r) : "d"(a));
+  return r;
+#else
+  return (a > 0.0) ? a : 0.0;
+#endif
+}
+EK_HD double dmin0(double a)
+{
+#if EK_ASM_MAX0 && defined(__CUDA_ARCH__)
+  double r;
+  asm("{\n\t.reg .pred p;\n\tsetp.lt.f64 p, %1, 0d0000000000000000;\n\tselp.f64 %0, %1, 0d0000000000000000, p;\n\t}" : "=d"(r) : "d"(a));
+  return r;
+#else
+  return (a < 0.0) ? a : 0.0;
+#endif
+}
+
 // Limited slope of the reference (slope_unsplit_hydro_{2d,3d}_scalar, HydroBaseFunctor3D.h:413-461;
 // same formula in MHDBaseFunctor3D.h:262-337 and for the face field in :563-668):
 //   dlft = st*(q-qm), drgt = st*(qp-q), dcen = (qp-qm)/2, dlim = (dlft*drgt <= 0) ? 0 : min(|dlft|,|drgt|),

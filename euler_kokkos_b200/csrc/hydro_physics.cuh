@@ -207,7 +207,7 @@ EK_HD void riemann_approx_n(const Grid& g, const double (*ql)[5], const double (
     cl[n] = gamma0 * pl[n] * rl[n];
     cr[n] = gamma0 * pr[n] * rr[n];
     const double wl = sqrt_pos_fast(cl[n]), wr = sqrt_pos_fast(cr[n]);
-    pold[n] = dmax(((wr * pl[n] + wl * pr[n]) + wl * wr * (ul[n] - ur[n])) * rcp_fast(wl + wr), 0.0);
+    pold[n] = dmax0(((wr * pl[n] + wl * pr[n]) + wl * wr * (ul[n] - ur[n])) * rcp_fast(wl + wr));
     ipl[n] = rcp_fast(pl[n]);
     ipr[n] = rcp_fast(pr[n]);
     active[n] = true; // conv = 1 > 1e-6
@@ -346,8 +346,8 @@ EK_HD void riemann_hll(const Grid& g, const double* __restrict__ ql, const doubl
   const double rr = dmax(qr[ID], g.smallr), ur = qr[IU], pr = dmax(qr[IP], rr * g.smallp);
   const double cl = sqrt(g.gamma0 * pl / rl);
   const double cr = sqrt(g.gamma0 * pr / rr);
-  const double SL = dmin(dmin(ul, ur) - dmax(cl, cr), 0.0);
-  const double SR = dmax(dmax(ul, ur) + dmax(cl, cr), 0.0);
+  const double SL = dmin0(dmin(ul, ur) - dmax(cl, cr));
+  const double SR = dmax0(dmax(ul, ur) + dmax(cl, cr));
   double uL[5], uR[5], fL[5], fR[5];
   hydro_cons_flux<DIM, true>(ql, entho, uL, fL);
   hydro_cons_flux<DIM, true>(qr, entho, uR, fR);

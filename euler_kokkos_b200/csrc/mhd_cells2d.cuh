@@ -66,8 +66,8 @@ EK_HD double mhd2d_stage_prims(const Grid& g, const double* __restrict__ U, doub
     const double c2 = g.gamma0 * q[IP] * rd;
     const double d2 = 0.5 * (b2 * rd + c2);
     const double d22 = d2 * d2, c2r = c2 * rd;
-    const double cfx = sqrt_fast(d2 + sqrt_fast(dmax(d22 - c2r * a * a, 0.0)));
-    const double cfy = sqrt_fast(d2 + sqrt_fast(dmax(d22 - c2r * b * b, 0.0)));
+    const double cfx = sqrt_fast(d2 + sqrt_fast(dmax0(d22 - c2r * a * a)));
+    const double cfy = sqrt_fast(d2 + sqrt_fast(dmax0(d22 - c2r * b * b)));
     return (cfx + fabs(q[IU])) * g.invdx + (cfy + fabs(q[IV])) * g.invdy;
   }
   return 0.0;

@@ -74,9 +74,9 @@ EK_HD double mhd_cell_invdt(const Grid& g, const double* __restrict__ q)
   const double c2 = g.gamma0 * q[IP] * rd;
   const double d2 = 0.5 * (b2 * rd + c2);
   const double d22 = d2 * d2, c2r = c2 * rd;
-  const double cfx = sqrt_fast(d2 + sqrt_fast(dmax(d22 - c2r * a * a, 0.0)));
-  const double cfy = sqrt_fast(d2 + sqrt_fast(dmax(d22 - c2r * b * b, 0.0)));
-  const double cfz = sqrt_fast(d2 + sqrt_fast(dmax(d22 - c2r * c * c, 0.0)));
+  const double cfx = sqrt_fast(d2 + sqrt_fast(dmax0(d22 - c2r * a * a)));
+  const double cfy = sqrt_fast(d2 + sqrt_fast(dmax0(d22 - c2r * b * b)));
+  const double cfz = sqrt_fast(d2 + sqrt_fast(dmax0(d22 - c2r * c * c)));
   return (cfx + fabs(q[IU])) * g.invdx + (cfy + fabs(q[IV])) * g.invdy + (cfz + fabs(q[IW])) * g.invdz;
 }
 
@@ -87,7 +87,7 @@ EK_HD double mhd_fast_speed2(double gamma0, double r, double p, double bn2, doub
   const double rd = rcp_fast(r);
   const double c2 = gamma0 * p * rd;
   const double d2 = 0.5 * ((bn2 + bt2sum) * rd + c2);
-  return d2 + sqrt_fast(dmax(d2 * d2 - c2 * bn2 * rd, 0.0));
+  return d2 + sqrt_fast(dmax0(d2 * d2 - c2 * bn2 * rd));
 }
 
 // ---- HLLD (Miyoshi & Kusano 2005), hydro components of the flux only --------------------------
@@ -236,8 +236,8 @@ EK_HD void mhd_hll(const Grid& g, const MhdSide& L, const MhdSide& R, double a, 
   const double a2 = a * a;
   const double cmax = sqrt_fast(dmax(mhd_fast_speed2(g.gamma0, L.r, L.p, a2, L.bt1 * L.bt1 + L.bt2 * L.bt2),
                                      mhd_fast_speed2(g.gamma0, R.r, R.p, a2, R.bt1 * R.bt1 + R.bt2 * R.bt2)));
-  const double sl = dmin(dmin(L.un, R.un) - cmax, 0.0);
-  const double sr = dmax(dmax(L.un, R.un) + cmax, 0.0);
+  const double sl = dmin0(dmin(L.un, R.un) - cmax);
+  const double sr = dmax0(dmax(L.un, R.un) + cmax);
   const double inv = rcp_fast(sr - sl);
 #pragma unroll
   for (int v = 0; v < (BT2 ? 6 : 5); ++v)
@@ -289,8 +289,8 @@ EK_HD double mhd_emf2d_hlld(const Grid& g, const MhdCorner& LL, const MhdCorner&
     const double c2 = gamma0 * s.p * rd;
     const double d2 = 0.5 * (bb * rd + c2);
     const double d22 = d2 * d2, c2r = c2 * rd;
-    cfx[n] = d2 + sqrt_fast(dmax(d22 - c2r * a2, 0.0)); // squares: the square root is taken after the max
-    cfy[n] = d2 + sqrt_fast(dmax(d22 - c2r * b2, 0.0));
+    cfx[n] = d2 + sqrt_fast(dmax0(d22 - c2r * a2)); // squares: the square root is taken after the max
+    cfy[n] = d2 + sqrt_fast(dmax0(d22 - c2r * b2));
     ptot[n] = s.p + 0.5 * bb;
   }
   const double cxm = sqrt_fast(dmax(dmax(cfx[0], cfx[1]), dmax(cfx[2], cfx[3])));
@@ -338,8 +338,8 @@ EK_HD double mhd_emf2d_hlld(const Grid& g, const MhdCorner& LL, const MhdCorner&
   const double calfvenT = dmax(dmax(dmax(fabs(LR.b) * rsqrt_fast(rstarLRy), fabs(BstarLR) * isLR),
                                     dmax(fabs(RR.b) * rsqrt_fast(rstarRRy), fabs(BstarRR) * isRR)), g.smallc);
 
-  const double SAL = dmin(ustar - calfvenL, 0.0), SAR = dmax(ustar + calfvenR, 0.0);
-  const double SAB = dmin(vstar - calfvenB, 0.0), SAT = dmax(vstar + calfvenT, 0.0);
+  const double SAL = dmin0(ustar - calfvenL), SAR = dmax0(ustar + calfvenR);
+  const double SAB = dmin0(vstar - calfvenB), SAT = dmax0(vstar + calfvenT);
   const double iSA_x = rcp_fast(SAR - SAL), iSA_y = rcp_fast(SAT - SAB);
 
   // the reference blends the five cases with 0/1 weights built from copysign(1, S): the sign BIT
