@@ -78,6 +78,7 @@ _protos = {
     "ek_launch_count": (C.c_int64, [_vp]),
     "ek_kernel_timing": (C.c_int, [_vp, C.c_int]),
     "ek_kernel_time": (C.c_int, [_vp, _dp, C.POINTER(C.c_int)]),
+    "ek_selftest_math": (C.c_int, [C.c_int, _vp, C.c_int, _vp]),
     "ek_comm_unique_id": (C.c_int, [_vp]),
     "ek_comm_attach": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.POINTER(C.c_int32)]),
     "ek_comm_detach": (C.c_int, [_vp]),
@@ -204,3 +205,13 @@ def comm_unique_id() -> bytes:
     if rc != EK_OK:
         raise EkError(f"ek_comm_unique_id failed ({rc})")
     return buf.raw
+
+
+def selftest_math(x: np.ndarray, device: int = 0) -> dict:
+    """device values of max(x,0), min(x,0), 1/x, sqrt(x), 1/sqrt(x), (1+x)/x for the operands x (ek_selftest_math)"""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.empty((6, x.size))
+    rc = lib.ek_selftest_math(device, _ptr(x), x.size, _ptr(out))
+    if rc != EK_OK:
+        raise EkError(f"ek_selftest_math failed ({rc}): {lib.ek_last_error(None).decode()}")
+    return dict(zip(("max0", "min0", "rcp", "sqrt", "rsqrt", "div"), out))

@@ -139,6 +139,22 @@ __global__ void __launch_bounds__(256) max_divb_kernel(const Grid g, const doubl
     atomic_max_nonneg(out_bits, m);
 }
 
+// device-side arithmetic primitives on caller-supplied operands (ek_selftest_math): the inline-PTX select forms and
+// the MUFU-seeded division / square roots of ek_common.cuh next to their IEEE counterparts
+__global__ void selftest_math_kernel(const double* __restrict__ x, int n, double* __restrict__ out)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  const double a = x[i];
+  out[i] = dmax0(a);
+  out[n + i] = dmin0(a);
+  out[2 * n + i] = rcp_fast(a);
+  out[3 * n + i] = sqrt_fast(a);
+  out[4 * n + i] = rsqrt_fast(a);
+  out[5 * n + i] = div_fast(1.0 + a, a);
+}
+
 // ---- helpers -------------------------------------------------------------------------------------
 static int validate(const ek_params& p, std::string& err)
 {
@@ -150,17 +166,31 @@ static int validate(const ek_params& p, std::string& err)
   if (p.dim == 2 && p.nz != 1) { err = "nz must be 1 in 2-D"; return EK_ERR_INVALID; }
   if (!(p.dx > 0) || !(p.dy > 0) || (p.dim == 3 && !(p.dz > 0))) { err = "dx,dy,dz must be > 0"; return EK_ERR_INVALID; }
   if (p.impl_version < 0 || p.impl_version > 2) { err = "implementationVersion must be 0,1,2"; return EK_ERR_INVALID; }
+  if (!(p.cfl > 0.0)) { err = "cfl must be > 0"; return EK_ERR_INVALID; }
+  if (!(p.gamma0 > 1.0)) { err = "gamma0 must be > 1 (entho = 1/(gamma0-1))"; return EK_ERR_INVALID; }
+  // slope_unsplit_hydro_{2d,3d} know slope_type 0 (no slopes), 1 and 2 only (HydroBaseFunctor3D.h:413-578,
+  // MHDBaseFunctor3D.h:364-495); anything else would give a limiter that is neither the reference's nor exact
+  if (!(p.slope_type == 0.0 || p.slope_type == 1.0 || p.slope_type == 2.0)) { err = "slope_type must be 0, 1 or 2"; return EK_ERR_INVALID; }
   if (!p.mhd) {
     const bool ok = p.riemann == EK_RIEMANN_APPROX || p.riemann == EK_RIEMANN_LLF || p.riemann == EK_RIEMANN_HLLC ||
                     (p.riemann == EK_RIEMANN_HLL && p.dim == 2);
     // the reference's 3-D dispatcher has no HLL branch and leaves the flux uninitialised
     // (shared/RiemannSolvers.h:610-633); hlld is MHD-only
     if (!ok) { err = "riemann solver not available for this hydro solver (RiemannSolvers.h:575-633)"; return EK_ERR_INVALID; }
-    if (!(p.slope_type == 0.0 || p.slope_type == 1.0 || p.slope_type == 2.0)) { err = "slope_type must be 0, 1 or 2"; return EK_ERR_INVALID; }
   } else {
     const bool ok = p.riemann == EK_RIEMANN_HLLD || p.riemann == EK_RIEMANN_HLL || p.riemann == EK_RIEMANN_LLF;
     if (!ok) { err = "riemann solver not available for MHD (RiemannSolvers_MHD.h:371-389)"; return EK_ERR_INVALID; }
     if (p.gravity_enabled) { err = "gravity is hydro-only in the reference"; return EK_ERR_INVALID; }
+    // implementationVersion 1 (3-D and 2-D) and 2 (2-D) are other schedules of the same arithmetic: the reference's
+    // own builds agree with its version 0 to <= 2e-15 (atomic-add order) and are served by the version-0 kernels.
+    // Version 2 in 3-D is a different scheme in the reference (MHDRunFunctors3D.h:865-1778): its results differ from
+    // versions 0/1 by up to 1e-1 on z-dependent problems (test_mhd_brio_wu_3d_z.ini).  It is not
+    // provided, and is refused rather than silently replaced.
+    if (p.dim == 3 && p.impl_version == 2) {
+      err = "MHD_Muscl_3D: implementationVersion=2 is not provided (the reference's version 2 differs from its versions 0/1 "
+            "on z-dependent problems, DESIGN.md section 7); use other/implementationVersion=0 or 1";
+      return EK_ERR_INVALID;
+    }
   }
   for (int f = 0; f < 6; ++f)
     if (p.bc[f] < 0 || p.bc[f] > EK_BC_COPY) { err = "bad boundary type"; return EK_ERR_INVALID; }
@@ -355,6 +385,8 @@ int ek_create(const ek_params* params, int device, ek_ctx** out)
     return EK_ERR_CUDA;
   }
   if (device < 0 || device >= ndev) { g_create_err = "device index out of range"; return EK_ERR_INVALID; }
+  int prev_device = -1;
+  cudaGetDevice(&prev_device); // restored before returning: creating a context must not move the caller's current device
   Ctx* c = new (std::nothrow) Ctx();
   if (!c) { g_create_err = "out of host memory"; return EK_ERR_INVALID; }
   c->p = *params;
@@ -367,6 +399,7 @@ int ek_create(const ek_params* params, int device, ek_ctx** out)
     if (e2 != cudaSuccess) {                                                       \
       g_create_err = std::string(#call) + ": " + cudaGetErrorString(e2);           \
       ek_destroy(reinterpret_cast<ek_ctx*>(c));                                    \
+      if (prev_device >= 0) cudaSetDevice(prev_device);                            \
       return EK_ERR_CUDA;                                                          \
     }                                                                              \
   } while (0)
@@ -408,6 +441,8 @@ int ek_create(const ek_params* params, int device, ek_ctx** out)
   CK(cudaMallocHost(&c->ts_host, sizeof(TimeState)));
   CK(cudaMalloc(&c->scratch, (64 + 2 * 8 * SUMS_BLOCKS) * sizeof(double)));
 #undef CK
+  if (prev_device >= 0)
+    cudaSetDevice(prev_device);
   *out = reinterpret_cast<ek_ctx*>(c);
   return EK_OK;
 }
@@ -443,7 +478,20 @@ int ek_set_stream(ek_ctx* ctx, void* cuda_stream)
 {
   if (!ctx) return EK_ERR_INVALID;
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
-  c->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+  cudaStream_t next = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+  if (next == c->stream)
+    return EK_OK;
+  // order the new stream after everything queued so far: the step stream and the helper streams whose results
+  // (middle chunks, halo planes) the next call reads
+  EK_CUDA(c, cudaSetDevice(c->device));
+  cudaStream_t prev[3] = { c->stream, c->aux_stream, c->comm_stream };
+  for (cudaStream_t st : prev) {
+    if (!st)
+      continue;
+    EK_CUDA(c, cudaEventRecord(c->ev_a, st));
+    EK_CUDA(c, cudaStreamWaitEvent(next, c->ev_a, 0));
+  }
+  c->stream = next;
   return EK_OK;
 }
 
@@ -633,6 +681,36 @@ int ek_conserved_sums(ek_ctx* ctx, double* sums_out)
   if (rc != EK_OK) return rc;
   EK_CUDA(c, cudaMemcpyAsync(sums_out, c->scratch, c->g.nbvar * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   EK_CUDA(c, cudaStreamSynchronize(c->stream));
+  return EK_OK;
+}
+
+int ek_selftest_math(int device, const double* x_host, int n, double* out_host)
+{
+  if (!x_host || !out_host || n <= 0) return EK_ERR_INVALID;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    g_create_err = "no CUDA device; this library has no CPU fallback";
+    return EK_ERR_CUDA;
+  }
+  int prev = -1;
+  cudaGetDevice(&prev);
+  double *dx = nullptr, *dout = nullptr;
+  cudaError_t e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaMalloc(&dx, (size_t)n * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&dout, (size_t)6 * n * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemcpy(dx, x_host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    selftest_math_kernel<<<(n + 127) / 128, 128>>>(dx, n, dout);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(out_host, dout, (size_t)6 * n * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(dx);
+  cudaFree(dout);
+  if (prev >= 0) cudaSetDevice(prev);
+  if (e != cudaSuccess) {
+    g_create_err = std::string("ek_selftest_math: ") + cudaGetErrorString(e);
+    return EK_ERR_CUDA;
+  }
   return EK_OK;
 }
 

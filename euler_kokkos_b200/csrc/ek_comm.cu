@@ -12,6 +12,8 @@
 #include <dlfcn.h>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <string>
 #include "ek_internal.h"
 
 namespace ek {
@@ -37,13 +39,8 @@ struct NcclApi {
   std::string err;
 };
 
-static NcclApi* nccl_api()
+static NcclApi* nccl_api_load(NcclApi& api)
 {
-  static NcclApi api;
-  static bool tried = false;
-  if (tried)
-    return api.h ? &api : nullptr;
-  tried = true;
   const char* names[] = { "libnccl.so.2", "libnccl.so" };
   for (const char* n : names) {
     api.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
@@ -75,6 +72,15 @@ static NcclApi* nccl_api()
   LD(GetErrorString, "ncclGetErrorString");
 #undef LD
   return &api;
+}
+
+// loaded once per process, also when several host threads each drive their own context
+static NcclApi* nccl_api()
+{
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] { nccl_api_load(api); });
+  return api.h ? &api : nullptr;
 }
 
 #define EK_NCCL(c, call)                                                              \

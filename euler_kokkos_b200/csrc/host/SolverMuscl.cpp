@@ -51,6 +51,7 @@ void SolverMusclB200::construct()
     for (int f = 0; f < 6; ++f)
       nb[f] = params.neighborsRank[f];
     check(ek_comm_attach(m_ctx, id, params.myRank, params.nProcs, nb), "ek_comm_attach");
+    rendezvous_done(params.myRank);
   }
   const size_t n = (size_t)ek_state_len(m_ctx);
   m_Uhost.assign(n, 0.0);
@@ -58,7 +59,12 @@ void SolverMusclB200::construct()
   if (params.gravity.enabled)
     grav.assign((size_t)isize * jsize * ksize * params.dimType, 0.0);
   // initial condition (host; cold path), then upload: sets U and U2 (deep_copy(U2,U))
-  init_problem(m_problem_name, params, configMap, m_Uhost.data(), grav.empty() ? nullptr : grav.data());
+  if (!init_problem(m_problem_name, params, configMap, m_Uhost.data(), grav.empty() ? nullptr : grav.data())) {
+    // restart_enabled=1 (HDF5/PnetCDF loaders are not part of this build) or an initial condition that does not
+    // exist for this solver: stop, as the reference does for configurations it cannot run (HydroParams.cpp:352-357)
+    fprintf(stderr, "[euler_b200] cannot initialise problem '%s' for solver %s\n", m_problem_name.c_str(), m_solver_name.c_str());
+    std::exit(EXIT_FAILURE);
+  }
   check(ek_upload_state(m_ctx, m_Uhost.data()), "ek_upload_state");
   if (!grav.empty())
     check(ek_set_gravity(m_ctx, grav.data()), "ek_set_gravity");
@@ -150,6 +156,11 @@ const std::vector<double>& SolverMusclB200::host_state()
 // SolverHydroMuscl::save_solution_impl (SolverHydroMuscl.h:751-762) -> save_VTK_{2D,3D}
 void SolverMusclB200::save_solution_impl()
 {
+  if (configMap.getBool("output", "outputVtkAscii", false)) {
+    // the reference's ascii branch (IO_VTK.cpp:306-338) is not provided: refuse rather than write another format
+    fprintf(stderr, "[euler_b200] output/outputVtkAscii=true is not supported (raw appended Float64 only)\n");
+    std::exit(EXIT_FAILURE);
+  }
   timers[TIMER_IO]->start();
   host_state();
   save_vti(m_Uhost.data(), params, configMap, params.nbvar, m_variables_names, m_times_saved);

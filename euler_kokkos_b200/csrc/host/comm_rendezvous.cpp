@@ -5,10 +5,21 @@
 #include <cstdlib>
 #include <string>
 #include <thread>
+#include <unistd.h>
 
 #include "../../../include/ek_b200.h"
 
 namespace euler_b200 {
+
+static std::string g_rdv_path;
+
+// called once ek_comm_attach has returned: ncclCommInitRank is collective, so every rank has read the id by then
+void rendezvous_done(int rank)
+{
+  if (rank == 0 && !g_rdv_path.empty())
+    std::remove(g_rdv_path.c_str());
+  g_rdv_path.clear();
+}
 
 void rendezvous_unique_id(int rank, int nranks, unsigned char* id128)
 {
@@ -16,10 +27,17 @@ void rendezvous_unique_id(int rank, int nranks, unsigned char* id128)
   if (const char* s = std::getenv("EK_RDV_FILE"))
     path = s;
   else {
+    // one file per LAUNCH: the ranks of one launch share their parent (torchrun's agent, mpirun, the shell), so its
+    // pid keys the file together with the rendezvous port and torchrun's run id.  A file left behind by an earlier
+    // launch therefore has another name, and rank 0 removes its own after the communicator is up (rendezvous_done).
     const char* port = std::getenv("MASTER_PORT");
-    path = std::string("/tmp/ek_b200_rdv_") + (port ? port : "0");
+    const char* run_id = std::getenv("TORCHELASTIC_RUN_ID");
+    path = std::string("/tmp/ek_b200_rdv_") + (port ? port : "0") + "_" + (run_id ? run_id : "none") + "_" +
+           std::to_string((long)getppid());
   }
+  g_rdv_path = path;
   if (rank == 0) {
+    std::remove(path.c_str()); // never publish on top of a stale file
     if (ek_comm_unique_id(id128) != EK_OK) {
       fprintf(stderr, "[euler_b200] NCCL is not available: cannot run on %d ranks\n", nranks);
       std::exit(EXIT_FAILURE);

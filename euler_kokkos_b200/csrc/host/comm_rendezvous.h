@@ -5,6 +5,9 @@
 
 namespace euler_b200 {
 //! rank 0 creates the id (ek_comm_unique_id) and publishes it; the others wait for it.
-//! The file is $EK_RDV_FILE or /tmp/ek_b200_rdv_<MASTER_PORT|0>.
+//! The file is $EK_RDV_FILE or /tmp/ek_b200_rdv_<MASTER_PORT|0>_<TORCHELASTIC_RUN_ID|none>_<pid of the launcher>:
+//! one name per launch, so a file left by an earlier launch on the same port is never read.
 void rendezvous_unique_id(int rank, int nranks, unsigned char* id128);
+//! after the communicator exists on every rank (ek_comm_attach returned): rank 0 removes the file.
+void rendezvous_done(int rank);
 } // namespace euler_b200

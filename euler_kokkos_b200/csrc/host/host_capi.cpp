@@ -9,9 +9,23 @@
 #include "IO_VTK.h"
 #include "InitConditions.h"
 #include "SolverFactory.h"
+#include "SolverMuscl.h"
 
 namespace euler_b200 {
 int run_ini(const std::string& input_file, const std::string& overrides);
+
+// a solver obtained from the factory together with the objects it refers to (what main() keeps on its stack)
+struct HostSolver {
+  ConfigMap configMap;
+  ParallelEnv env;
+  HydroParams* params = nullptr;
+  SolverBase* solver = nullptr;
+  ~HostSolver()
+  {
+    delete solver;
+    delete params;
+  }
+};
 
 struct HostCase {
   ConfigMap configMap;
@@ -113,6 +127,54 @@ int ekh_case_save_vti(void* h, const double* U, int step, char* path_out, int ca
   return 0;
 }
 int ekh_solver_registered(const char* name) { return SolverFactory::Instance().has(name) ? 1 : 0; }
+// ---- the SolverBase surface main() and solver_utils use (src/main.cpp:112-153), one call per member -------------
+// SolverFactory::Instance().create(run/solver_name, params, configMap) on an ini file (+ overrides)
+void* ekh_solver_create(const char* ini_path, const char* overrides)
+{
+  HostSolver* s = new HostSolver();
+  s->configMap = ConfigMap(ini_path);
+  if (s->configMap.ParseError() < 0) {
+    delete s;
+    return nullptr;
+  }
+  if (overrides)
+    s->configMap.applyOverrides(overrides);
+  s->env = ParallelEnv::fromEnvironment();
+  s->params = new HydroParams(s->configMap, s->env);
+  const std::string name = s->configMap.getString("run", "solver_name", "Unknown");
+  if (!SolverFactory::Instance().has(name)) { // create() would abort the process (SolverFactory.h:105-113)
+    delete s;
+    return nullptr;
+  }
+  s->solver = SolverFactory::Instance().create(name, *s->params, s->configMap);
+  return s;
+}
+void ekh_solver_destroy(void* h) { delete static_cast<HostSolver*>(h); }
+int ekh_solver_finished(void* h) { return static_cast<HostSolver*>(h)->solver->finished(); }
+void ekh_solver_next_iteration(void* h) { static_cast<HostSolver*>(h)->solver->next_iteration(); }
+int ekh_solver_advance(void* h, int n) { return static_cast<HostSolver*>(h)->solver->advance(n); }
+void ekh_solver_save_solution(void* h) { static_cast<HostSolver*>(h)->solver->save_solution(); }
+// out[0]=m_t, out[1]=m_dt, out[2]=m_iteration, out[3]=m_times_saved, out[4]=m_nCells, out[5]=state length (doubles)
+int ekh_solver_info(void* h, double* out)
+{
+  if (!h || !out) return 1;
+  SolverBase* b = static_cast<HostSolver*>(h)->solver;
+  out[0] = b->m_t; out[1] = b->m_dt; out[2] = b->m_iteration; out[3] = b->m_times_saved; out[4] = (double)b->m_nCells;
+  SolverMusclB200* m = dynamic_cast<SolverMusclB200*>(b);
+  out[5] = m ? (double)ek_state_len(m->context()) : 0.0;
+  return 0;
+}
+// current state, ghosts included, SoA [var][k][j][i]
+int ekh_solver_state(void* h, double* U, long long cap)
+{
+  if (!h || !U) return 1;
+  SolverMusclB200* m = dynamic_cast<SolverMusclB200*>(static_cast<HostSolver*>(h)->solver);
+  if (!m) return 2;
+  const std::vector<double>& u = m->host_state();
+  if ((long long)u.size() > cap) return 3;
+  std::memcpy(U, u.data(), u.size() * sizeof(double));
+  return 0;
+}
 // the whole driver (main.cpp) as a function
 int ekh_run_ini(const char* ini_path, const char* overrides) { return run_ini(ini_path, overrides ? overrides : ""); }
 

@@ -33,9 +33,21 @@ hlib.ekh_case_save_vti.argtypes = [_vp, _vp, C.c_int, C.c_char_p, C.c_int]
 hlib.ekh_solver_registered.argtypes = [C.c_char_p]
 hlib.ekh_run_ini.argtypes = [C.c_char_p, C.c_char_p]
 
+hlib.ekh_solver_create.restype = _vp
+hlib.ekh_solver_create.argtypes = [C.c_char_p, C.c_char_p]
+hlib.ekh_solver_destroy.argtypes = [_vp]
+hlib.ekh_solver_finished.argtypes = [_vp]
+hlib.ekh_solver_next_iteration.argtypes = [_vp]
+hlib.ekh_solver_advance.argtypes = [_vp, C.c_int]
+hlib.ekh_solver_save_solution.argtypes = [_vp]
+hlib.ekh_solver_info.argtypes = [_vp, C.POINTER(C.c_double)]
+hlib.ekh_solver_state.argtypes = [_vp, _vp, C.c_longlong]
+
 HOST_SYMBOLS = ("ekh_case_create", "ekh_case_destroy", "ekh_case_params", "ekh_case_neighbors", "ekh_case_run_info",
                 "ekh_case_get_string", "ekh_case_get_float", "ekh_case_init_state", "ekh_case_write_ini",
-                "ekh_solver_registered", "ekh_run_ini")
+                "ekh_solver_registered", "ekh_run_ini", "ekh_solver_create", "ekh_solver_destroy", "ekh_solver_finished",
+                "ekh_solver_next_iteration", "ekh_solver_advance", "ekh_solver_save_solution", "ekh_solver_info",
+                "ekh_solver_state")
 
 
 def _ov(overrides) -> bytes:
@@ -138,6 +150,58 @@ class Case:
             return ("mhd step kernels (mhd_pet + mhd_faces_edges_call + mhd_update)" if self.params.dim == 3
                     else "mhd2d step kernels (prims + elec + trace + faces_edge + update)")
         return f"hydro_step_kernel<{self.params.dim}>"
+
+
+class Solver:
+    """SolverFactory::create(run/solver_name, ...) on an ini file: the object the reference's main() drives
+    (src/main.cpp:112-153) -- finished(), next_iteration(), save_solution(), m_t / m_dt / m_iteration -- plus the
+    device-resident advance(n) and a copy of the current state."""
+
+    def __init__(self, ini_path: str, overrides=None):
+        self._h = hlib.ekh_solver_create(ini_path.encode(), _ov(overrides))
+        if not self._h:
+            raise ValueError(f"{ini_path}: unreadable, or run/solver_name is not a registered solver")
+        self.case = Case(ini_path, overrides)
+
+    def close(self):
+        if self._h:
+            hlib.ekh_solver_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _info(self):
+        out = (C.c_double * 8)()
+        hlib.ekh_solver_info(self._h, out)
+        return out
+
+    t = property(lambda self: self._info()[0])
+    dt = property(lambda self: self._info()[1])
+    iteration = property(lambda self: int(self._info()[2]))
+    times_saved = property(lambda self: int(self._info()[3]))
+
+    def finished(self) -> bool:
+        return bool(hlib.ekh_solver_finished(self._h))
+
+    def next_iteration(self):
+        hlib.ekh_solver_next_iteration(self._h)
+
+    def advance(self, n: int) -> int:
+        return hlib.ekh_solver_advance(self._h, int(n))
+
+    def save_solution(self):
+        hlib.ekh_solver_save_solution(self._h)
+
+    def state(self) -> np.ndarray:
+        U = np.zeros(self.case.params.shape)
+        rc = hlib.ekh_solver_state(self._h, U.ctypes.data_as(_vp), U.size)
+        if rc != 0:
+            raise RuntimeError(f"ekh_solver_state failed (rc={rc})")
+        return U
 
 
 def write_ini(src_ini: str, overrides, dst_path: str):

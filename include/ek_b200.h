@@ -148,6 +148,12 @@ int64_t ek_launch_count(const ek_ctx* ctx);
 int ek_kernel_timing(ek_ctx* ctx, int enable);
 int ek_kernel_time(ek_ctx* ctx, double* total_ms_out, int* launches_out);
 
+/* Arithmetic self-test of the device primitives the kernels are built from (csrc/ek_common.cuh): for each of the n
+ * operands x[i] writes max(x,0), min(x,0) (the setp/selp forms), 1/x, sqrt(x), 1/sqrt(x) and (1+x)/x (MUFU seed +
+ * Newton steps) to out[0..6n).  The tests compare them with IEEE arithmetic on +-0, denormals, +-inf, NaN and random
+ * operands; nothing in the reference corresponds to it. */
+int ek_selftest_math(int device, const double* x_host, int n, double* out_host);
+
 /* ---- multi-GPU: z-slab (or mx*my*mz) decomposition, halos over NCCL/NVLink -------------------- */
 /* Replaces src/shared/mpiBorderUtils.h + SolverBase::transfer_boundaries_* (MPI_Sendrecv,
  * src/shared/SolverBase.cpp:756-845) and MPI_Allreduce<MIN> (SolverBase.cpp:134-138). */

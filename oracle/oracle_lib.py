@@ -140,7 +140,8 @@ def run_reference(ini_path: str, cwd: str, threads: int | None = None, timeout: 
     """Run the UNMODIFIED reference binary on an ini file inside `cwd`; returns its stdout."""
     env = dict(os.environ)
     env["OMP_NUM_THREADS"] = str(threads or os.cpu_count() or 1)
-    env.setdefault("OMP_PROC_BIND", "false")
+    env.setdefault("OMP_PROC_BIND", "spread")  # BASELINE.md section 2
+    env.setdefault("OMP_PLACES", "threads")
     r = subprocess.run([REF_BIN, ini_path], cwd=cwd, env=env, capture_output=True, text=True, timeout=timeout)
     if r.returncode != 0:
         raise RuntimeError(f"reference binary failed ({r.returncode}):\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}")

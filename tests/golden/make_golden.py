@@ -70,6 +70,11 @@ CASES = {
     "briowu2d_x_hlld": (R + "test_mhd_brio_wu_2d_x.ini", {"mesh.nx": 64, "mesh.ny": 8, "other.implementationversion": 0}, 8, (1, 8)),
     "briowu2d_y_hlld": (R + "test_mhd_brio_wu_2d_y.ini", {"mesh.nx": 8, "mesh.ny": 48, "other.implementationversion": 0}, 6, (1, 6)),
     "briowu3d_z_hlld": (R + "test_mhd_brio_wu_3d_z.ini", {"mesh.nx": 8, "mesh.ny": 8, "mesh.nz": 48, "other.implementationversion": 0}, 6, (1, 6)),
+    # MHD implementationVersion 1 / 2 exactly as the shipped files ask for it (no override of [other]): served by the
+    # version-0 kernels (the reference's versions agree to 2e-15 in these configurations)
+    "mhdblast3d_hlld_impl1": (R + "test_mhd_blast_3D.ini", {"mesh.nx": 16, "mesh.ny": 12, "mesh.nz": 12, "blast.radius": 0.3}, 6, (1, 6)),
+    "briowu2d_x_hlld_impl2": (R + "test_mhd_brio_wu_2d_x.ini", {"mesh.nx": 64, "mesh.ny": 8}, 8, (1, 8)),
+    "briowu2d_y_hlld_impl2": (R + "test_mhd_brio_wu_2d_y.ini", {"mesh.nx": 8, "mesh.ny": 48}, 6, (1, 6)),
     "rotor2d_hlld": (R + "test_mhd_rotor.ini", {"mesh.nx": 40, "mesh.ny": 40}, 5, (1, 5)),
     "fieldloop2d_hlld": (R + "mhd_fieldloop2d.ini", {"mesh.nx": 32, "mesh.ny": 20, "hydro.problem": "field_loop"}, 5, (1, 5)),
     "fieldloop3d_hlld": (R + "mhd_fieldloop3d.ini", {"mesh.nx": 24, "mesh.ny": 12, "mesh.nz": 12, "hydro.problem": "field_loop"}, 4, (1, 4)),

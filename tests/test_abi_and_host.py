@@ -54,6 +54,32 @@ def test_invalid_parameters_are_rejected_before_touching_the_gpu():
     p = util.make_params(dim=3, riemann="hll")  # no HLL branch in the reference's 3-D hydro dispatcher
     with pytest.raises(capi.EkError):
         capi.Context(p)
+    # slope_type is checked for both solver families; cfl and gamma0 must make sense (entho = 1/(gamma0-1))
+    for kw, field, bad in ((dict(mhd=True, riemann="hlld"), "slope_type", 3.0), (dict(mhd=True, riemann="hlld"), "slope_type", 0.5),
+                           (dict(), "slope_type", 1.5), (dict(), "cfl", 0.0), (dict(), "cfl", -0.5), (dict(), "gamma0", 1.0),
+                           (dict(mhd=True, riemann="hlld"), "gamma0", 0.9)):
+        p = util.make_params(**kw)
+        setattr(p, field, bad)
+        with pytest.raises(capi.EkError, match=field):
+            capi.Context(p)
+
+
+def test_mhd_implementation_versions():
+    """MHD implementationVersion 1 (2-D, 3-D) and 2 (2-D) are schedules of the same arithmetic as version 0 in the
+    reference (its own builds agree to 2e-15) and are accepted; version 2 in 3-D is a different scheme there (results
+    differ by up to 1e-1 on z-dependent problems) and is refused, not silently replaced."""
+    from euler_kokkos_b200 import capi
+    from tests import util
+
+    p = util.make_params(dim=3, mhd=True, riemann="hlld", impl=2)
+    with pytest.raises(capi.EkError, match="implementationVersion=2 is not provided"):
+        capi.Context(p)
+    for dim, impl in ((3, 1), (2, 1), (2, 2)):
+        p = util.make_params(dim=dim, mhd=True, riemann="hlld", impl=impl)
+        try:
+            capi.Context(p).close()
+        except capi.EkError as e:  # no device here: validation passed, the allocation did not
+            assert "no CUDA device" in str(e), e
 
 
 def _case(text, overrides=None):

@@ -31,7 +31,24 @@ def test_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
     assert d["cpu_baseline"]["value"] == d["value"] == d["e2e"]["value"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
-    assert "test_blast_3D.ini" in d["config"]["workload"]
+    assert "test_mhd_orszag_tang_3D.ini @ 512x512x512" in d["config"]["workload"]  # the north-star target, same string as our arm
+    assert "128x128x128" in d["cpu_baseline"]["sample"]
+
+
+def test_reference_arm_does_not_load_the_product_libraries():
+    """the ini of the sample is edited in plain Python: neither capi (libek_b200.so) nor hostapi (libek_host.so) is
+    imported by the process that times the reference"""
+    from oracle import oracle_lib as O
+
+    if not O.have_reference():
+        pytest.skip("oracle/_ref is not built here")
+    code = ("import sys, argparse; sys.path.insert(0, %r); import bench; "
+            "a = argparse.Namespace(workload='implode2d', n=None, shape=None); "
+            "v, desc, thr = bench.reference_sample(a, None, 5, threads=2); assert v > 0; "
+            "bad = [m for m in sys.modules if m.startswith('euler_kokkos_b200')]; assert not bad, bad; "
+            "maps = open('/proc/self/maps').read(); assert 'libek_' not in maps; print('ok')") % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
 
 
 def test_our_arm_has_no_cpu_fallback():

@@ -2,6 +2,8 @@
 semantics, synthetic states, and the parity metric of SURVEY.md section 8(c)."""
 from __future__ import annotations
 
+import re
+
 import numpy as np
 
 from euler_kokkos_b200 import capi
@@ -97,3 +99,16 @@ def group_rel_linf(a, b, p):
         den = max(np.abs(bi[idx]).max(), 1e-300)
         out[name] = float(np.abs(ai[idx] - bi[idx]).max() / den)
     return out
+
+
+def edit_ini(text: str, **kv) -> str:
+    """replace 'key=value' lines (keys are unique across sections in these files)"""
+    for k, v in kv.items():
+        text, n = re.subn(rf"(?m)^{k}=.*$", f"{k}={v}", text)
+        assert n == 1, (k, n)
+    return text
+
+
+def log_lines(out: str):
+    return [ln.rstrip() for ln in out.splitlines() if ln.startswith("time step=") or ln.startswith("Output results at time")
+            or ln.startswith("final time is")]
