@@ -92,7 +92,8 @@ std::string save_vti(const double* U, const HydroParams& params, const ConfigMap
   // global cell extents of this piece; the origin is the global one (the pieces are placed by their extents)
   const int x0 = params.myMpiPos[0] * nx, y0 = params.myMpiPos[1] * ny, z0 = three_d ? params.myMpiPos[2] * nz : 0;
   const double ox = params.xmin, oy = params.ymin, oz = params.zmin;
-  out << "<VTKFile type=\"ImageData\" version=\"" << (pieces ? "1.0" : "0.1") << "\" byte_order=\"LittleEndian\" header_type=\"UInt64\">\n";
+  // the reference writes version 0.1 only from its serial 3-D writer (IO_VTK.cpp:298-302; 2-D :100-104 and the MPI pieces :513-517, :737-741 say 1.0)
+  out << "<VTKFile type=\"ImageData\" version=\"" << ((pieces || !three_d) ? "1.0" : "0.1") << "\" byte_order=\"LittleEndian\" header_type=\"UInt64\">\n";
   if (three_d) {
     out << "  <ImageData WholeExtent=\"" << x0 << " " << x0 + nx << " " << y0 << " " << y0 + ny << " " << z0 << " " << z0 + nz << "\" "
         << "Origin=\"" << ox << " " << oy << " " << oz << "\" "
