@@ -3,6 +3,7 @@
 
     python bench.py --gpus N --steps K --warmup W [--workload ot3d|blast3d|implode2d|rt3d|ot2d] [--n 512]
     python bench.py --impl reference ...      # the reference's own CPU (OpenMP) build, same metric and config
+    python bench.py --impl reference-cuda ... # the reference's own Kokkos-Cuda build on one B200 (same-box GPU comparator)
 
 A "step" is one godunov_unsplit over the whole (local) grid.  The default workload is the north-star target,
 BASELINE.json configs[2]: test_mhd_orszag_tang_3D.ini scaled to 512^3 (MHD_Muscl_3D, HLLD + constrained transport).
@@ -499,6 +500,49 @@ def run_reference_arm(args):
     emit(line)
 
 
+def run_reference_cuda_arm(args):
+    """The reference's OWN GPU build (oracle/_ref_cuda: unmodified sources, Kokkos Cuda backend, -arch=sm_100) on one
+    B200 of the same box: the GPU-vs-GPU comparator.  One run of the binary on the workload at the largest size its
+    work arrays allow (MHD impl 0 needs ~1.66 KB per cell: 512^3 does not fit 180 GB, 384^3 does); the figure is its own
+    Perf line converted to interior cells.  None of the product libraries is loaded."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    binary = os.path.join(ROOT, "oracle", "_ref_cuda", "euler_kokkos_cuda")
+    if not os.path.exists(binary):
+        emit({"impl": "reference-cuda", "unavailable": "oracle/_ref_cuda/euler_kokkos_cuda is not built (make -C oracle/ref_build -f Makefile.cuda)"})
+        return
+    w = WORKLOADS[args.workload]
+    n = args.n or {"mhd": 384}.get(w["fam"], w["n"])
+    nsteps = args.warmup + args.steps
+    with tempfile.TemporaryDirectory() as td:
+        extra = {"run.nstepmax": nsteps, "run.tend": 1e6, "run.nlog": 1000000, "output.outputdir": td}
+        if w["n"] is not None:
+            extra.update({"mesh.nx": n, "mesh.ny": n, "mesh.nz": n})
+        ini, _ = workload_ini(args, extra)
+        path = os.path.join(td, "case.ini")
+        ini.write(path)
+        t0 = time.time()
+        r = subprocess.run([binary, path], cwd=td, capture_output=True, text=True, timeout=3000)
+        wall = time.time() - t0
+    out = r.stdout
+    m = re.search(r"Perf\s*:\s*([0-9.eE+-]+)\s*number of Mcell-updates/s", out)
+    if r.returncode != 0 or not m:
+        emit({"impl": "reference-cuda", "unavailable": f"run failed (rc={r.returncode}): {(out + r.stderr)[-400:]}"})
+        return
+    _, dim, gw, nx, ny, nz = ini_geometry(ini)
+    ghosted = (nx + 2 * gw) * (ny + 2 * gw) * ((nz + 2 * gw) if dim == 3 else 1)
+    value = float(m.group(1)) * 1e6 * (nx * ny * nz) / ghosted
+    tt = re.search(r"total\s+time\s*:\s*([0-9.eE+-]+)", out)
+    cargs = argparse.Namespace(**vars(args))
+    cargs.n = n
+    emit({"impl": "reference-cuda", "metric": "cell-updates/s (FP64)", "value": value, "unit": "cell-updates/s", "n_gpus": 1,
+          "steps": nsteps, "warmup": 0, "ms_per_step": (float(tt.group(1)) * 1e3 / nsteps) if tt else None,
+          "higher_is_better": True, "dtype": "f64", "data": "synthetic (analytic initial condition of the ini file)",
+          "config": config_dict(cargs, 1), "wall_s": wall,
+          "what": "unmodified reference, Kokkos 5.1 Cuda backend, nvcc -arch=sm_100 (oracle/ref_build/Makefile.cuda); its own Perf "
+                  "line (all steps incl. the first, total-time timer) converted to interior cells"})
+
+
 _REAL_STDOUT = None
 
 
@@ -526,7 +570,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"])
     ap.add_argument("--workload", default="ot3d", choices=sorted(WORKLOADS))
     ap.add_argument("--n", "--size", dest="n", type=int, default=None, help="cubic interior size per GPU (default 512); use --size under torchrun, whose own parser claims --n")
     ap.add_argument("--shape", default=None, help="per-GPU interior box NX,NY,NZ of a 3-D workload (overrides --n)")
@@ -538,6 +582,8 @@ def main():
     protect_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.impl == "reference-cuda":
+        run_reference_cuda_arm(args)
     else:
         run_ours(args)
 

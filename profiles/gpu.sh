@@ -43,6 +43,10 @@ for STEP in "$@"; do
       F=$O/${TAG}_bench_n$A.json
       timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $A --master-addr 127.0.0.1 --master-port 29533 \
         bench.py --gpus $A --steps 10 --warmup 3 $(args "$B") > $F 2> ${F%.json}.err; echo "[$STEP] bench rc=$?"; cut -c1-420 $F ;;
+    refcuda)   # the reference's own Kokkos-Cuda build on this GPU: hydro blast 512^3 and MHD Orszag-Tang 384^3
+      timeout 900 python bench.py --impl reference-cuda --workload blast3d --steps 20 --warmup 3 > $O/${TAG}_refcuda_blast3d.json 2> $O/${TAG}_refcuda_blast3d.err; cut -c1-300 $O/${TAG}_refcuda_blast3d.json
+      timeout 900 python bench.py --impl reference-cuda --workload ot3d --steps 10 --warmup 3 > $O/${TAG}_refcuda_ot3d.json 2> $O/${TAG}_refcuda_ot3d.err; cut -c1-300 $O/${TAG}_refcuda_ot3d.json
+      timeout 900 python bench.py --workload ot3d --size 384 --steps 10 --no-cpu-baseline > $O/${TAG}_bench_ot3d_384.json 2> $O/${TAG}_bench_ot3d_384.err; cut -c1-300 $O/${TAG}_bench_ot3d_384.json ;;
     dropin)
       python - > $O/${TAG}_dropin.ini <<'PY'
 import sys

@@ -93,3 +93,94 @@ def test_mhd3d_two_slabs_periodic_match_single_domain(tmp_path, monkeypatch, ove
     """overlap=1: the update stage does the END planes first and their exchange runs beside the update of the rest"""
     monkeypatch.setenv("EK_HALO_OVERLAP", overlap)
     _run_case("test_mhd_orszag_tang_3D.ini", {"mesh.nx": 32, "mesh.ny": 32}, 12, 2, 8, tmp_path, 1e-13)
+
+
+# ---- mx x my x mz decompositions ([mpi] section of the ini, HydroParams.cpp:186-320): packed x / y halos ------------
+def _worker_cart(rank, world, uid, ini, overrides, nsteps, outdir):
+    import torch  # noqa: F401
+
+    from euler_kokkos_b200 import capi, hostapi
+
+    torch.cuda.set_device(rank)
+    case = hostapi.Case(ini, overrides, rank=rank, nranks=world)
+    p = case.params
+    U, grav = case.new_state()
+    ctx = capi.Context(p, rank)
+    if grav is not None:
+        ctx.set_gravity(grav)
+    ctx.comm_attach(uid, rank, world, case.neighbors)
+    ctx.upload(U)
+    t, dt, n = ctx.run(nsteps)
+    np.savez(os.path.join(outdir, f"rank{rank}.npz"), U=ctx.download(), t=t, pos=np.array(case.mpi_pos), sums=ctx.conserved_sums())
+    ctx.close()
+
+
+def _run_cart(ini_name, ov_local, dims, nsteps, tmp_path, tol):
+    """every rank owns an nx x ny x nz box of an (mx*nx) x (my*ny) x (mz*nz) grid; the assembled result must equal the
+    single-domain run (the reference's MPI layout: mpiBorderUtils.h:36-330, SolverBase.cpp:583-664)"""
+    import torch
+    import torch.multiprocessing as mp
+
+    world = dims[0] * dims[1] * dims[2]
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    from euler_kokkos_b200 import capi, hostapi
+    from euler_kokkos_b200.vti import interior_of
+
+    ini = hostapi.settings(ini_name)
+    uid = capi.comm_unique_id()
+    ov = dict(ov_local)
+    ov.update({"mpi.mx": dims[0], "mpi.my": dims[1], "mpi.mz": dims[2]})
+    mp.spawn(_worker_cart, args=(world, uid, ini, ov, nsteps, str(tmp_path)), nprocs=world, join=True)
+
+    ov1 = dict(ov_local)
+    ov1.update({"mesh.nx": ov_local["mesh.nx"] * dims[0], "mesh.ny": ov_local["mesh.ny"] * dims[1], "mesh.nz": ov_local["mesh.nz"] * dims[2]})
+    case = hostapi.Case(ini, ov1)
+    p = case.params
+    U, grav = case.new_state()
+    ctx = capi.Context(p, 0)
+    if grav is not None:
+        ctx.set_gravity(grav)
+    ctx.upload(U)
+    t1, _, _ = ctx.run(nsteps)
+    ref = interior_of(ctx.download(), p.ghost, p.dim)
+    sums1 = ctx.conserved_sums()
+    ctx.close()
+
+    nx, ny, nz = ov_local["mesh.nx"], ov_local["mesh.ny"], ov_local["mesh.nz"]
+    got = np.full_like(ref, np.nan)
+    for r in range(world):
+        z = np.load(os.path.join(str(tmp_path), f"rank{r}.npz"))
+        assert abs(float(z["t"]) - t1) <= 1e-14 * abs(t1)
+        np.testing.assert_allclose(z["sums"], sums1, rtol=1e-12, atol=1e-12 * abs(sums1[0]))
+        px, py, pz = (int(v) for v in z["pos"])
+        got[:, pz * nz:(pz + 1) * nz, py * ny:(py + 1) * ny, px * nx:(px + 1) * nx] = interior_of(z["U"], p.ghost, p.dim)
+    assert not np.isnan(got).any()
+    den = np.abs(ref).max(axis=(1, 2, 3), keepdims=True) + 1e-300
+    err = (np.abs(got - ref) / den).max()
+    assert err <= tol, err
+
+
+@pytest.mark.parametrize("dims", [(2, 1, 1), (1, 2, 1)])
+def test_hydro3d_x_and_y_halos_on_two_gpus(tmp_path, dims):
+    """packed (non-contiguous) ghost slabs: halo_copy_kernel + ncclSend/Recv along x, along y"""
+    _run_cart("test_implode_3D.ini", {"mesh.nx": 24, "mesh.ny": 20, "mesh.nz": 16}, dims, 8, tmp_path, 1e-13)
+
+
+@pytest.mark.parametrize("dims", [(2, 1, 1), (1, 2, 1)])
+def test_mhd3d_x_and_y_halos_on_two_gpus(tmp_path, dims):
+    _run_cart("test_mhd_orszag_tang_3D.ini", {"mesh.nx": 20, "mesh.ny": 16, "mesh.nz": 12}, dims, 6, tmp_path, 1e-13)
+
+
+def test_hydro3d_2x2x2_on_eight_gpus(tmp_path):
+    """the layout of test_implode_3D_mpi.ini ([mpi] mx, my, mz > 1 in every direction), reflective outer faces"""
+    _run_cart("test_implode_3D.ini", {"mesh.nx": 20, "mesh.ny": 16, "mesh.nz": 16}, (2, 2, 2), 10, tmp_path, 1e-13)
+
+
+def test_mhd3d_2x2x2_periodic_on_eight_gpus(tmp_path):
+    """periodic wrap in all three directions between the 8 sub-domains, corner / edge ghosts through the X -> Y -> Z order"""
+    _run_cart("test_mhd_orszag_tang_3D.ini", {"mesh.nx": 16, "mesh.ny": 16, "mesh.nz": 12}, (2, 2, 2), 6, tmp_path, 1e-13)
+
+
+def test_mhd2d_2x2_on_four_gpus(tmp_path):
+    _run_cart("test_mhd_orszag_tang_2D.ini", {"mesh.nx": 32, "mesh.ny": 24, "mesh.nz": 1}, (2, 2, 1), 8, tmp_path, 1e-13)
