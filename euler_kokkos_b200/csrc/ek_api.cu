@@ -300,7 +300,7 @@ static int enqueue_step(Ctx& c, int use_host_dt, double host_dt, int max_steps)
     c.launches++;
     c.mhd_dt_partial_for = mhd_dt_folded(c) ? Uout : nullptr; // the update kernel reduces the new level
     ktime_mark(c);
-    if (c.overlap_ok && !mhd_pipelined(c)) {
+    if (c.overlap_ok) {
       // every stage, the update of the END planes first; they travel to the z neighbours beside the update of the rest
       EK_CUDA(&c, launch_mhd_step(c, Uin, Uout, 1));
       EK_CUDA(&c, cudaEventRecord(c.ev_edge, c.stream));
@@ -456,7 +456,6 @@ int ek_destroy(ek_ctx* ctx)
   ek_comm_detach(ctx);
   for (cudaEvent_t e : c->kev) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamSynchronize(c->own_stream);
-  mhd_pipe_destroy(*c);
   if (c->aux_stream) cudaStreamSynchronize(c->aux_stream);
   if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
   cudaFree(c->U[0]); cudaFree(c->U[1]); cudaFree(c->grav); cudaFree(c->work); cudaFree(c->ts); cudaFree(c->scratch);

@@ -39,10 +39,8 @@ struct Ctx {
   // level whose CFL maximum (all interior cells but the last layers) the update kernel has left in ts->invdt_bits
   const double* mhd_dt_partial_for = nullptr;
   int sm_count = 148;
-  // slab-pipelined MHD step (mhd_launch.cu, EK_MHD_PIPE): streams of the P+E+T (two, alternating), R and U stages
-  // and the events that order slab s of one stage after the slabs it reads from the stage before
-  cudaStream_t pipe_stream[4] = { nullptr, nullptr, nullptr, nullptr };
-  std::vector<cudaEvent_t> pipe_ev;
+  const void* smem_attr_for = nullptr; // hydro step kernel whose dynamic shared-memory limit has been raised on this device
+  bool mhd_pet_attr = false; // dynamic shared-memory limit of mhd_pet_kernel raised on this device
   // communicator (z-slab / cartesian neighbours)
   void* nccl_comm = nullptr;
   int rank = 0, nranks = 1;
@@ -76,8 +74,6 @@ cudaError_t launch_mhd_step(Ctx& c, const double* Uin, double* Uout, int part = 
 cudaError_t launch_mhd_invdt(Ctx& c, const double* U);
 cudaError_t launch_mhd_invdt_layers(Ctx& c, const double* U);
 bool mhd_dt_folded(const Ctx& c);
-bool mhd_pipelined(const Ctx& c);
-void mhd_pipe_destroy(Ctx& c);
 size_t mhd_work_bytes(const Grid& g);
 // ek_comm.cu
 int comm_exchange_dir(Ctx& c, double* U, int dir, cudaStream_t stream = nullptr); // halo exchange along one direction

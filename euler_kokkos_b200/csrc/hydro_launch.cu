@@ -3,7 +3,6 @@
 #include "ek_internal.h"
 #include <cstdlib>
 #include "hydro_kernels.cuh"
-#include "hydro_kernels_1b.cuh"
 
 namespace ek {
 
@@ -20,9 +19,6 @@ constexpr int TY = EK_HYDRO_TY;
 #define EK_HYDRO_TYF 14
 #endif
 constexpr int TYF = EK_HYDRO_TYF;
-// EK_HYDRO_FOLD=2: folded rows with 15 warps = 480 threads, 14 of them solving, spread 4/4/3/3 over the schedulers
-// (measured: 11.8 ms per step on blast 512^3 against 10.9 -- the scheduler imbalance costs more than the tile gains)
-constexpr int TYF2 = 13;
 
 // 3-D tile layout: 1 = folded halo rows, 28 x 14 tile, 16 warps; 0 = one warp per tile row incl. halo rows, 28 x 11,
 // 15 warps.  Measured at 512^3 (profiles/r01_hydro_fold_ncu.txt): the folded layout executes 3.4 % fewer
@@ -35,16 +31,7 @@ static int fold_rows(int riemann)
   const int v = getenv("EK_HYDRO_FOLD") ? atoi(getenv("EK_HYDRO_FOLD")) : -1;
   if (v < 0)
     return riemann == RIEMANN_APPROX ? TYF : 0;
-  return v == 0 ? 0 : (v == 2 ? TYF2 : TYF);
-}
-
-// 3-D schedule: 0 (default) = two block barriers per plane (hydro_kernels.cuh); 1 = the one-barrier software
-// pipeline of hydro_kernels_1b.cuh (measured 1.7 % slower at 512^3: the barrier stalls ncu reports belong to the
-// halo-row warps, which have nothing else to do)
-static bool use_1b()
-{
-  const int v = getenv("EK_HYDRO_1B") ? atoi(getenv("EK_HYDRO_1B")) : 0;
-  return v != 0;
+  return v == 0 ? 0 : TYF;
 }
 
 // z-chunk length: enough CTAs to fill whole waves over the SMs, long enough to amortise the
@@ -61,7 +48,7 @@ static int pick_zchunk(int nz, long long xy_ctas, int sm_count, int min_chunks =
     const long long ctas = xy_ctas * real_chunks;
     const long long waves = (ctas + sm_count - 1) / sm_count;
     const double tail = (double)(waves * sm_count) / (double)ctas; // idle-SM factor of the last wave
-    const double warm = (double)(zc + (use_1b() ? 3.5 : 2.5)) / (double)zc; // pipeline warm-up per chunk
+    const double warm = (double)(zc + 2.5) / (double)zc; // pipeline warm-up per chunk
     const double cost = tail * warm;
     if (cost < best_cost - 1e-12) {
       best_cost = cost;
@@ -97,7 +84,7 @@ static ZPlan z_plan(const Ctx& c, long long xy_ctas, bool want_split)
   return z;
 }
 
-static int tile_rows(int dim, int riemann) { return (dim == 3 && fold_rows(riemann) > 0 && !use_1b()) ? fold_rows(riemann) : TY; }
+static int tile_rows(int dim, int riemann) { return (dim == 3 && fold_rows(riemann) > 0) ? fold_rows(riemann) : TY; }
 static long long hydro_xy_ctas(const Grid& g, int riemann)
 {
   const int ty = tile_rows(g.nz > 1 ? 3 : 2, riemann);
@@ -113,12 +100,6 @@ static cudaError_t launch_one(Ctx& c, const double* Uin, double* Uout, int part,
   using Smem = HydroSmem<DIM, TY>;
   void (*kern)(const HydroArgs) = hydro_step_kernel<DIM, RS, TY, GRAV>;
   size_t smem = sizeof(Smem);
-  if constexpr (DIM == 3 && RS != RIEMANN_HLL) {
-    if (use_1b()) {
-      kern = hydro_step1b_kernel<RS, TY, GRAV>;
-      smem = sizeof(HydroSmem1b<TY>);
-    }
-  }
   int ty = TY, warps = TY + 4;
   if constexpr (DIM == 3) {
     const int tr = tile_rows(3, RS);
@@ -127,20 +108,15 @@ static cudaError_t launch_one(Ctx& c, const double* Uin, double* Uout, int part,
       smem = sizeof(HydroSmem<DIM, TYF>);
       ty = TYF;
       warps = TYF + 2;
-    } else if (tr == TYF2) {
-      kern = hydro_step_kernel<DIM, RS, TYF2, GRAV, 1>;
-      smem = sizeof(HydroSmem<DIM, TYF2>);
-      ty = TYF2;
-      warps = TYF2 + 2;
     }
   }
-  const int variant = (DIM == 3 && ty == TYF) ? 2 : (DIM == 3 && ty == TYF2) ? 3 : (use_1b() ? 1 : 0);
-  static bool attr_done[16][4] = { { false } };
-  if (!attr_done[c.device & 15][variant]) {
+  // (idempotent; set on every launch path rather than cached in a static, so that contexts on several host threads
+  //  cannot race on a flag)
+  if (c.smem_attr_for != (const void*)kern) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess)
       return e;
-    attr_done[c.device & 15][variant] = true;
+    c.smem_attr_for = (const void*)kern;
   }
   HydroArgs a;
   a.g = c.g;

@@ -94,16 +94,11 @@ struct MhdChunkMap {
   unsigned yc;     // rows per slab
   unsigned nchunk; // slabs
   unsigned span;   // threads per slab-plane: yc*isize rounded up to tiles + 1 tile
-  unsigned kg;     // consecutive planes handled by consecutive warps (one CTA = kg warps = the same 32-cell
-                   // segment in kg planes: the k-1 / k+1 lines of one warp are the own lines of its CTA mates => L1 hits)
-  unsigned kpad;   // ksize rounded up to a multiple of kg
 };
-EK_HD MhdChunkMap mhd_chunk_map(const Grid& g, int yc, int kg = 1)
+EK_HD MhdChunkMap mhd_chunk_map(const Grid& g, int yc)
 {
   MhdChunkMap m;
   m.yc = (yc <= 0) ? 0u : (unsigned)(yc < g.jsize ? yc : g.jsize);
-  m.kg = (kg < 1) ? 1u : (unsigned)kg;
-  m.kpad = (((unsigned)g.ksize + m.kg - 1) / m.kg) * m.kg;
   if (m.yc == 0) {
     m.nchunk = 1;
     m.span = 0;
@@ -117,7 +112,7 @@ EK_HD unsigned long long mhd_chunk_threads(const Grid& g, const MhdChunkMap& m)
 {
   if (m.yc == 0)
     return (unsigned long long)g.sv;
-  return (unsigned long long)m.nchunk * m.kpad * m.span;
+  return (unsigned long long)m.nchunk * (unsigned)g.ksize * m.span;
 }
 EK_HD bool mhd_chunk_cell(const Grid& g, const MhdChunkMap& m, unsigned t, MhdIdx& x)
 {
@@ -130,21 +125,13 @@ EK_HD bool mhd_chunk_cell(const Grid& g, const MhdChunkMap& m, unsigned t, MhdId
     if (c >= (unsigned)g.sv)
       return false;
   } else {
-    const unsigned per_chunk = m.span * m.kpad;
+    const unsigned per_chunk = m.span * (unsigned)g.ksize;
     const unsigned ch = t / per_chunk;
     if (ch >= m.nchunk)
       return false;
     const unsigned r = t - ch * per_chunk;
-    // inside a slab: groups of kg planes; inside a group: 32-cell segment (slowest), plane, lane
-    const unsigned per_group = m.span * m.kg;
-    const unsigned kgi = r / per_group;
-    const unsigned rr = r - kgi * per_group;
-    const unsigned seg = rr / (32u * m.kg);
-    const unsigned rw = rr - seg * (32u * m.kg);
-    const unsigned k = kgi * m.kg + (rw >> 5);
-    if (k >= (unsigned)g.ksize)
-      return false;
-    const unsigned o = seg * 32u + (rw & 31u);
+    const unsigned k = r / m.span; // inside a slab: plane (slowest), then the cells of the slab-plane
+    const unsigned o = r - k * m.span;
     const unsigned j0 = ch * m.yc;
     const unsigned j1 = (j0 + m.yc < (unsigned)g.jsize) ? j0 + m.yc : (unsigned)g.jsize;
     const unsigned c0 = sj * j0 + sk * k;       // first cell of the slab-plane

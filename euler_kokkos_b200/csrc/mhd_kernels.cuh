@@ -1,12 +1,9 @@
-// CUDA kernels of the CT-MHD step: thin thread->cell mappings over the per-cell stages of
-// mhd_cells.cuh.  One thread per cell of the ghosted box, flattened index (i fastest => coalesced,
-// no partially filled blocks along x for sizes like 518).
+// CUDA kernels of the CT-MHD step: thin thread->cell mappings over the per-cell stages of mhd_cells.cuh (3-D: stage U
+// and the CFL passes here, stages P+E+T in mhd_pet.cuh, stage R in mhd_stage_r.cuh; 2-D: all five stages here).
+// One thread per cell of the ghosted box, flattened index (i fastest => coalesced, no partially filled blocks along x
+// for sizes like 518).
 #pragma once
 #include "mhd_cells2d.cuh"
-
-#ifndef EK_MHD_TRACE_PREFETCH
-#define EK_MHD_TRACE_PREFETCH 1
-#endif
 
 namespace ek {
 
@@ -20,7 +17,6 @@ struct MhdArgs {
   unsigned t0 = 0; // offset added to the linear thread index (launches restricted to a range of planes / of y-slabs)
   unsigned t1 = 0xffffffffu; // one past the last linear thread index this launch may take
   int upd_klo = 0, upd_khi = 1 << 30; // planes [upd_klo, upd_khi) the update kernel may write
-  int r_pf = 0; // stage R: L2 prefetch of the compact state this many planes ahead (0 = off)
 };
 
 __device__ __forceinline__ bool mhd_cell_of_thread(const MhdArgs& a, MhdIdx& x)
@@ -47,29 +43,22 @@ __device__ __forceinline__ bool mhd_cell_of_thread(const Grid& g, MhdIdx& x)
   return true;
 }
 
-// stage P + CFL max-reduction (warp shuffles, then one atomic per CTA: grid reduce)
-// store_q = 0: CFL reduction only (the fused P+E+T kernel recomputes the primitives it needs)
-__global__ void __launch_bounds__(256) mhd_prims_kernel(const MhdArgs a, const int do_invdt, const int store_q = 1)
+// CFL max-reduction of a ghost-filled level (first step / ek_compute_dt; inside the time loop the update kernel carries
+// it): primitives of every interior cell on the fly, warp shuffles, then one atomic per CTA (grid reduce)
+__global__ void __launch_bounds__(256) mhd_invdt_kernel(const MhdArgs a)
 {
   if (a.ts->finished)
     return;
-  const MhdWork w = mhd_work_split(a.work, a.g.sv);
   MhdIdx x;
   double m = 0.0;
   if (mhd_cell_of_thread(a.g, x)) {
-    if (store_q) {
-      m = mhd_stage_prims(a.g, a.Uin, w.Q, x);
-    } else {
-      const int gw = a.g.gw;
-      if (x.i >= gw && x.i < a.g.isize - gw && x.j >= gw && x.j < a.g.jsize - gw && x.k >= gw && x.k < a.g.ksize - gw) {
-        double q[8];
-        mhd_prims_at(a.g, a.Uin, x, q);
-        m = mhd_cell_invdt(a.g, q);
-      }
+    const int gw = a.g.gw;
+    if (x.i >= gw && x.i < a.g.isize - gw && x.j >= gw && x.j < a.g.jsize - gw && x.k >= gw && x.k < a.g.ksize - gw) {
+      double q[8];
+      mhd_prims_at(a.g, a.Uin, x, q);
+      m = mhd_cell_invdt(a.g, q);
     }
   }
-  if (!do_invdt)
-    return;
   __shared__ double red[8];
   m = warp_max(m);
   if ((threadIdx.x & 31) == 0)
@@ -80,83 +69,6 @@ __global__ void __launch_bounds__(256) mhd_prims_kernel(const MhdArgs a, const i
     r = warp_max(r);
     if (threadIdx.x == 0 && r > 0.0)
       atomic_max_nonneg(&a.ts->invdt_bits, r);
-  }
-}
-
-__global__ void __launch_bounds__(256) mhd_elec_kernel(const MhdArgs a)
-{
-  if (a.ts->finished)
-    return;
-  const MhdWork w = mhd_work_split(a.work, a.g.sv);
-  MhdIdx x;
-  if (mhd_cell_of_thread(a, x))
-    mhd_stage_elec(a.g, a.Uin, w.Q, w.E, x);
-}
-
-#ifndef EK_MHD_TRACE_MINB
-#define EK_MHD_TRACE_MINB 3
-#endif
-__global__ void __launch_bounds__(256, EK_MHD_TRACE_MINB) mhd_trace_kernel(const MhdArgs a)
-{
-  if (a.ts->finished)
-    return;
-  const MhdWork w = mhd_work_split(a.work, a.g.sv);
-  const double dt = a.ts->dt;
-  MhdIdx x;
-  if (mhd_cell_of_thread(a, x)) {
-#if EK_MHD_TRACE_PREFETCH
-    // the stage walks x, then y, then z: pull the y/z neighbour lines of Q towards L2 while the x
-    // part waits on DRAM (the kernel is latency bound: ~80 independent loads per cell, 80 registers)
-    if (x.i >= 2 && x.j >= 2 && x.k >= 2 && x.i <= a.g.isize - 3 && x.j <= a.g.jsize - 3 && x.k <= a.g.ksize - 3) {
-      const double* qn[4] = { w.Q + tile_off<8>(x.c - x.sj), w.Q + tile_off<8>(x.c + x.sj), w.Q + tile_off<8>(x.c - x.sk),
-                              w.Q + tile_off<8>(x.c + x.sk) };
-#pragma unroll
-      for (int n = 0; n < 4; ++n)
-#pragma unroll
-        for (int v = 0; v < 8; ++v)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(qn[n] + TL * v));
-    }
-#endif
-    mhd_stage_trace(a.g, a.Uin, w.Q, w.E, w.S, dt / a.g.dx, dt / a.g.dy, dt / a.g.dz, x);
-  }
-}
-
-template <int RS>
-__global__ void __launch_bounds__(128) mhd_flux_kernel(const MhdArgs a)
-{
-  if (a.ts->finished)
-    return;
-  const MhdWork w = mhd_work_split(a.work, a.g.sv);
-  MhdIdx x;
-  if (mhd_cell_of_thread(a, x))
-    mhd_stage_fluxes<RS>(a.g, w.S, w.F, x);
-}
-
-__global__ void __launch_bounds__(128) mhd_emf_kernel(const MhdArgs a)
-{
-  if (a.ts->finished)
-    return;
-  const MhdWork w = mhd_work_split(a.work, a.g.sv);
-  MhdIdx x;
-  if (mhd_cell_of_thread(a, x))
-    mhd_stage_emfs(a.g, w.S, w.EMF, x);
-}
-
-// stage R in one pass: the three face fluxes, then the three edge EMFs of the same cell (the S
-// lines of the cell and its neighbours are read once from HBM and served from L1/L2 the second time)
-#ifndef EK_MHD_R_MINB
-#define EK_MHD_R_MINB 4
-#endif
-template <int RS>
-__global__ void __launch_bounds__(128, EK_MHD_R_MINB) mhd_faces_edges_kernel(const MhdArgs a)
-{
-  if (a.ts->finished)
-    return;
-  const MhdWork w = mhd_work_split(a.work, a.g.sv);
-  MhdIdx x;
-  if (mhd_cell_of_thread(a, x)) {
-    mhd_stage_fluxes<RS>(a.g, w.S, w.F, x);
-    mhd_stage_emfs(a.g, w.S, w.EMF, x);
   }
 }
 
@@ -316,5 +228,5 @@ __global__ void __launch_bounds__(256) mhd2d_update_kernel(const MhdArgs a)
 
 } // namespace ek
 
-#include "mhd_staged.cuh"
+#include "mhd_stage_r.cuh"
 #include "mhd_pet.cuh"

@@ -24,7 +24,7 @@ struct PetSmem {
 };
 
 template <int DUMMY = 0>
-__global__ void __launch_bounds__(PET_TX* PET_TY, 2) mhd_pet_kernel(const MhdArgs a, const int zchunk, const int l2_prefetch, const int ty0 = 0)
+__global__ void __launch_bounds__(PET_TX* PET_TY, 2) mhd_pet_kernel(const MhdArgs a, const int zchunk)
 {
   extern __shared__ __align__(16) unsigned char pet_raw[];
   PetSmem& sm = *reinterpret_cast<PetSmem*>(pet_raw);
@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(PET_TX* PET_TY, 2) mhd_pet_kernel(const MhdArg
   const double dt = a.ts->dt;
   const double dtdx = dt / g.dx, dtdy = dt / g.dy, dtdz = dt / g.dz;
   const int t = threadIdx.x;
-  const int i0 = 2 + PET_TX * blockIdx.x, j0 = 2 + PET_TY * ((int)blockIdx.y + ty0); // ty0: first tile row of this launch // first cell of the tile (ghosted coordinates)
+  const int i0 = 2 + PET_TX * blockIdx.x, j0 = 2 + PET_TY * (int)blockIdx.y; // first cell of the tile (ghosted coordinates)
   const int kbeg = 2 + (int)blockIdx.z * zchunk;
   const int kend = min(kbeg + zchunk, g.ksize - 1); // the predictor runs on planes 2 .. ksize-2
   if (kbeg >= kend)
@@ -151,24 +151,6 @@ __global__ void __launch_bounds__(PET_TX* PET_TY, 2) mhd_pet_kernel(const MhdArg
   __syncthreads();
 
   for (int p = kbeg; p < kend; ++p) {
-    if (l2_prefetch && p + 3 < g.ksize - 1) {
-      // the conserved state this thread converts next iteration: ask L2 for it now (first touch comes from DRAM)
-      MhdIdx x;
-      cell_of_box(bA, p + 3, x);
-      if (x.i < g.isize && x.j < g.jsize) {
-#pragma unroll
-        for (int v = 0; v < 8; ++v)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.Uin + g.sv * v + x.c));
-      }
-      if (hasB) {
-        cell_of_box(bB, p + 3, x);
-        if (x.i < g.isize && x.j < g.jsize) {
-#pragma unroll
-          for (int v = 0; v < 8; ++v)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.Uin + g.sv * v + x.c));
-        }
-      }
-    }
     {
       MhdIdx x;
       if (trace_cell(p, x)) {

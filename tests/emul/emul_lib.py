@@ -28,7 +28,7 @@ def lib():
         _lib.emul_hydro_invdt.restype = C.c_double
         _lib.emul_hydro_invdt.argtypes = [C.c_void_p, dp, dp]
         _lib.emul_chunk_map_check.restype = C.c_longlong
-        _lib.emul_chunk_map_check.argtypes = [C.c_int] * 5
+        _lib.emul_chunk_map_check.argtypes = [C.c_int] * 4
     return _lib
 
 
@@ -65,8 +65,8 @@ def mhd_invdt_layers(p, U):
     return lib().emul_mhd_invdt_layers(C.byref(p), _dp(U))
 
 
-def chunk_map_violations(isize, jsize, ksize, yc, kg=1):
-    return lib().emul_chunk_map_check(isize, jsize, ksize, yc, kg)
+def chunk_map_violations(isize, jsize, ksize, yc):
+    return lib().emul_chunk_map_check(isize, jsize, ksize, yc)
 
 
 def hydro_step(p, U, dt, grav=None):

@@ -125,12 +125,12 @@ int emul_mhd_step(const ek_params* p, const double* Uin, double* Uout, double* w
 // the y-chunked launch order of the 3-D stencil kernels (mhd_chunk_cell): every cell of the ghosted box
 // must be produced by exactly one thread, with thread%32 == cell%32 (warps aligned to the AoSoA tiles).
 // Returns the number of violations.
-long long emul_chunk_map_check(int isize, int jsize, int ksize, int yc, int kg)
+long long emul_chunk_map_check(int isize, int jsize, int ksize, int yc)
 {
   Grid g{};
   g.isize = isize; g.jsize = jsize; g.ksize = ksize;
   g.sj = isize; g.sk = (long long)isize * jsize; g.sv = g.sk * ksize;
-  const MhdChunkMap m = mhd_chunk_map(g, yc, kg);
+  const MhdChunkMap m = mhd_chunk_map(g, yc);
   const unsigned long long nt = mhd_chunk_threads(g, m);
   std::vector<unsigned char> seen((size_t)g.sv, 0);
   long long bad = 0;

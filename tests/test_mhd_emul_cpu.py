@@ -64,13 +64,12 @@ def test_emul_random_states_2d(riemann, bc):
 
 @pytest.mark.parametrize("shape,yc", [((70, 70, 22), 32), ((38, 37, 14), 8), ((134, 29, 9), 5), ((22, 18, 30), 0), ((22, 18, 30), 18),
                                       ((518, 70, 6), 32), ((33, 65, 7), 64)])
-@pytest.mark.parametrize("kg", [1, 4, 8])
-def test_chunked_launch_order_covers_every_cell_once(shape, yc, kg):
+def test_chunked_launch_order_covers_every_cell_once(shape, yc):
     """mhd_chunk_cell (the thread -> cell map of the 3-D stencil kernels): a bijection onto the ghosted box that
     keeps warps aligned with the AoSoA tiles."""
     from tests.emul import emul_lib as E
 
-    assert E.chunk_map_violations(*shape, yc, kg) == 0
+    assert E.chunk_map_violations(*shape, yc) == 0
 
 
 @pytest.mark.parametrize("bc", [(3, 3, 3, 3, 3, 3), (1, 1, 2, 2, 1, 2)])

@@ -112,15 +112,11 @@ def test_mhd3d_divb_and_conservation():
     assert d0 < 1e-11 and d1 < 1e-11, (d0, d1)
 
 
-@pytest.mark.parametrize("knobs", [{"EK_MHD_STAGED": "0"}, {"EK_MHD_STAGED": "1"}, {"EK_MHD_STAGED": "2", "EK_MHD_YCHUNK": "0"},
-                                   {"EK_MHD_YCHUNK": "5", "EK_MHD_ZGROUP": "1"}, {"EK_MHD_FUSE_R": "0", "EK_MHD_STAGED": "0"},
-                                   {"EK_MHD_PET": "0"}, {"EK_MHD_PET_PF": "1"}, {"EK_MHD_DTFOLD": "0"},
-                                   {"EK_MHD_PIPE": "1"}, {"EK_MHD_PIPE": "1", "EK_MHD_YCHUNK": "8"},
-                                   {"EK_MHD_PIPE": "2", "EK_MHD_YCHUNK": "8", "EK_MHD_DTFOLD": "0"}])
+@pytest.mark.parametrize("knobs", [{"EK_MHD_YCHUNK": "0"}, {"EK_MHD_YCHUNK": "5"}, {"EK_MHD_YCHUNK": "16"}, {"EK_MHD_DTFOLD": "0"}])
 def test_mhd3d_kernel_variants_agree_with_the_oracle(knobs, monkeypatch):
-    """every selectable variant of stage R (inlined / cp.async-staged / solver calls), of the launch order (flat,
-    y-chunked, z-grouped), of stages P+E+T (three kernels / fused, its L2-prefetch flavour), of the
-    CFL reduction and of the slab-pipelined launch (2 and 4 pipeline stages on this grid) is held to the same one-step tolerance."""
+    """the launch orders of stage R / U (flat, y-chunked) and both placements of the CFL reduction are held to the same
+    one-step tolerance (the variants that lost in round 1 -- cp.async-staged and fully inlined stage R, z-grouped order,
+    L2 prefetches, three-kernel P/E/T, the slab-pipelined launch -- are gone; DESIGN.md keeps their measurements)"""
     for k, v in knobs.items():
         monkeypatch.setenv(k, v)
     p = util.make_params(dim=3, mhd=True, n=(45, 26, 19), riemann="hlld", bc=(3, 3, 1, 2, 2, 1), smallr=1e-8, smallc=1e-8,
