@@ -435,6 +435,7 @@ int ek_create(const ek_params* params, int device, ek_ctx** out)
     c->work_bytes = mhd_work_bytes(c->g);
     if (c->work_bytes)
       CK(cudaMalloc(&c->work, c->work_bytes));
+    mhd_make_tensor_maps(*c); // optional: without them the plain-load P+E+T kernel is used
   }
   CK(cudaMalloc(&c->ts, sizeof(TimeState)));
   CK(cudaMemset(c->ts, 0, sizeof(TimeState)));

@@ -1,5 +1,6 @@
 // Internal (non-ABI) declarations shared by the translation units of libek_b200.so.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <string>
 #include <vector>
@@ -41,6 +42,11 @@ struct Ctx {
   int sm_count = 148;
   const void* smem_attr_for = nullptr; // hydro step kernel whose dynamic shared-memory limit has been raised on this device
   bool mhd_pet_attr = false; // dynamic shared-memory limit of mhd_pet_kernel raised on this device
+  // TMA descriptors of the two time levels as 4-D tensors (x, y, z, variable) for the TMA-fed P+E+T kernel
+  // (mhd_pet_tma.cuh); valid when the row stride is a multiple of 16 bytes and the driver provides the encoder
+  alignas(64) CUtensorMap umap[2];
+  bool umap_ok = false;
+  bool mhd_pet_tma_attr = false;
   // communicator (z-slab / cartesian neighbours)
   void* nccl_comm = nullptr;
   int rank = 0, nranks = 1;
@@ -75,6 +81,7 @@ cudaError_t launch_mhd_invdt(Ctx& c, const double* U);
 cudaError_t launch_mhd_invdt_layers(Ctx& c, const double* U);
 bool mhd_dt_folded(const Ctx& c);
 size_t mhd_work_bytes(const Grid& g);
+bool mhd_make_tensor_maps(Ctx& c); // false: TMA path unavailable for this grid / driver (the plain-load kernel serves it)
 // ek_comm.cu
 int comm_exchange_dir(Ctx& c, double* U, int dir, cudaStream_t stream = nullptr); // halo exchange along one direction
 int comm_allreduce_invdt(Ctx& c);                        // max over ranks of ts->invdt_bits

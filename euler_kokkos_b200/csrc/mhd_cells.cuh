@@ -281,6 +281,20 @@ EK_HD void mhd_stage_elec(const Grid& g, const double* __restrict__ U, const dou
 struct MhdTraceIn {
   const double *Q0, *Qxm, *Qxp, *Qym, *Qyp, *Qzm, *Qzp;
   const double *E0, *Ei, *Ej, *Ek;
+  // the access interface mhd_trace_core is written against (mhd_pet_tma.cuh has a second implementation that forms the
+  // cell-centred field from face values held in shared memory): primitive variable v of the cell / of a neighbour,
+  // component c of the edge field of the cell / of its +x, +y, +z neighbour
+  EK_HD double q0(int v) const { return Q0[TL * v]; }
+  EK_HD double qxm(int v) const { return Qxm[TL * v]; }
+  EK_HD double qxp(int v) const { return Qxp[TL * v]; }
+  EK_HD double qym(int v) const { return Qym[TL * v]; }
+  EK_HD double qyp(int v) const { return Qyp[TL * v]; }
+  EK_HD double qzm(int v) const { return Qzm[TL * v]; }
+  EK_HD double qzp(int v) const { return Qzp[TL * v]; }
+  EK_HD double e0(int c) const { return E0[TL * c]; }
+  EK_HD double ei(int c) const { return Ei[TL * c]; }
+  EK_HD double ej(int c) const { return Ej[TL * c]; }
+  EK_HD double ek(int c) const { return Ek[TL * c]; }
 };
 
 EK_HD bool mhd_trace_active(const Grid& g, const MhdIdx& x)
@@ -324,33 +338,30 @@ EK_HD void mhd_trace_load(const Grid& g, const double* __restrict__ U, const Mhd
 }
 
 // Sc: tile pointer of the cell's compact state (output)
-EK_HD void mhd_trace_core(const Grid& g, const MhdTraceB& fb, const MhdTraceIn& P, double* __restrict__ Sc, double dtdx,
+template <class IN>
+EK_HD void mhd_trace_core(const Grid& g, const MhdTraceB& fb, const IN& P, double* __restrict__ Sc, double dtdx,
                           double dtdy, double dtdz, const MhdIdx& x)
 {
-  const double* __restrict__ E0 = P.E0;
   const bool in_i = x.i <= g.isize - 3, in_j = x.j <= g.jsize - 3, in_k = x.k <= g.ksize - 3;
   const double xst = dmin(g.slope_type, 2.0); // slope_unsplit_mhd_3d, MHDBaseFunctor3D.h:600
 
   const double AL = fb.A0, BL = fb.B0, CL = fb.C0;
-  const double ELL = E0[0], FLL = E0[TL], GLL = E0[2 * TL];
-  const double* __restrict__ Ei = P.Ei;
-  const double* __restrict__ Ej = P.Ej;
-  const double* __restrict__ Ek = P.Ek;
+  const double ELL = P.e0(0), FLL = P.e0(1), GLL = P.e0(2);
   // face-centred half step: AL + sAL0 etc. (:872-877, :889-894) and halved transverse slopes (:810-822)
   if (in_j && in_k) {
-    const double GLR = Ej[2 * TL], FLR = Ek[TL];
+    const double GLR = P.ej(2), FLR = P.ek(1);
     Sc[TL * SFA] = AL + (+(GLR - GLL) * dtdy * 0.5 - (FLR - FLL) * dtdz * 0.5);
     Sc[TL * SDAY] = mhd_half_slope(0.5 * xst, g.slope_k, fb.Aym, AL, fb.Ayp);
     Sc[TL * SDAZ] = mhd_half_slope(0.5 * xst, g.slope_k, fb.Azm, AL, fb.Azp);
   }
   if (in_i && in_k) {
-    const double GRL = Ei[2 * TL], ELR = Ek[0];
+    const double GRL = P.ei(2), ELR = P.ek(0);
     Sc[TL * SFB] = BL + (-(GRL - GLL) * dtdx * 0.5 + (ELR - ELL) * dtdz * 0.5);
     Sc[TL * SDBX] = mhd_half_slope(0.5 * xst, g.slope_k, fb.Bxm, BL, fb.Bxp);
     Sc[TL * SDBZ] = mhd_half_slope(0.5 * xst, g.slope_k, fb.Bzm, BL, fb.Bzp);
   }
   if (in_i && in_j) {
-    const double FRL = Ei[TL], ERL = Ej[0];
+    const double FRL = P.ei(1), ERL = P.ej(0);
     Sc[TL * SFC] = CL + (+(FRL - FLL) * dtdx * 0.5 - (ERL - ELL) * dtdy * 0.5);
     Sc[TL * SDCX] = mhd_half_slope(0.5 * xst, g.slope_k, fb.Cxm, CL, fb.Cxp);
     Sc[TL * SDCY] = mhd_half_slope(0.5 * xst, g.slope_k, fb.Cym, CL, fb.Cyp);
@@ -363,22 +374,19 @@ EK_HD void mhd_trace_core(const Grid& g, const MhdTraceB& fb, const MhdTraceIn& 
   const double st = g.slope_type;
   const double sth = 0.5 * st;
   const bool use_slopes = (st == 1.0 || st == 2.0); // slope_unsplit_hydro_3d, :379,:470
-  const double* __restrict__ Q0 = P.Q0;
   double q[8];
 #pragma unroll
   for (int v = 0; v < 8; ++v)
-    q[v] = Q0[TL * v];
+    q[v] = P.q0(v);
   const double r = q[ID], p = q[IP], u = q[IU], v = q[IV], w = q[IW], A = q[IA], B = q[IB], C = q[IC];
   const double ir = rcp_fast(r);
   const double gp = g.gamma0 * p;
   double sr0, sp0, su0, sv0, sw0, sA0, sB0, sC0;
   {
-    const double* __restrict__ Qm = P.Qxm;
-    const double* __restrict__ Qp = P.Qxp;
     double d[8];
 #pragma unroll
     for (int n = 0; n < 8; ++n)
-      d[n] = (use_slopes && n != IA) ? mhd_half_slope(sth, g.slope_k, Qm[TL * n], q[n], Qp[TL * n]) : 0.0;
+      d[n] = (use_slopes && n != IA) ? mhd_half_slope(sth, g.slope_k, P.qxm(n), q[n], P.qxp(n)) : 0.0;
     const double drx = d[ID], dpx = d[IP], dux = d[IU], dvx = d[IV], dwx = d[IW], dBx = d[IB], dCx = d[IC];
     const double dAx = 0.5 * (fb.Axp - AL);
     sr0 = (-u * drx - dux * r) * dtdx;
@@ -392,12 +400,10 @@ EK_HD void mhd_trace_core(const Grid& g, const MhdTraceB& fb, const MhdTraceIn& 
     Sc[TL * (SX + 5)] = dBx; Sc[TL * (SX + 6)] = dCx;
   }
   {
-    const double* __restrict__ Qm = P.Qym;
-    const double* __restrict__ Qp = P.Qyp;
     double d[8];
 #pragma unroll
     for (int n = 0; n < 8; ++n)
-      d[n] = (use_slopes && n != IB) ? mhd_half_slope(sth, g.slope_k, Qm[TL * n], q[n], Qp[TL * n]) : 0.0;
+      d[n] = (use_slopes && n != IB) ? mhd_half_slope(sth, g.slope_k, P.qym(n), q[n], P.qyp(n)) : 0.0;
     const double dry = d[ID], dpy = d[IP], duy = d[IU], dvy = d[IV], dwy = d[IW], dAy = d[IA], dCy = d[IC];
     const double dBy = 0.5 * (fb.Byp - BL);
     sr0 += (-v * dry - dvy * r) * dtdy;
@@ -411,12 +417,10 @@ EK_HD void mhd_trace_core(const Grid& g, const MhdTraceB& fb, const MhdTraceIn& 
     Sc[TL * (SY + 5)] = dAy; Sc[TL * (SY + 6)] = dCy;
   }
   {
-    const double* __restrict__ Qm = P.Qzm;
-    const double* __restrict__ Qp = P.Qzp;
     double d[8];
 #pragma unroll
     for (int n = 0; n < 8; ++n)
-      d[n] = (use_slopes && n != IC) ? mhd_half_slope(sth, g.slope_k, Qm[TL * n], q[n], Qp[TL * n]) : 0.0;
+      d[n] = (use_slopes && n != IC) ? mhd_half_slope(sth, g.slope_k, P.qzm(n), q[n], P.qzp(n)) : 0.0;
     const double drz = d[ID], dpz = d[IP], duz = d[IU], dvz = d[IV], dwz = d[IW], dAz = d[IA], dBz = d[IB];
     const double dCz = 0.5 * (fb.Czp - CL);
     sr0 += (-w * drz - dwz * r) * dtdz;

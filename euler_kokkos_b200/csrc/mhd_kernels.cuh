@@ -230,3 +230,4 @@ __global__ void __launch_bounds__(256) mhd2d_update_kernel(const MhdArgs a)
 
 #include "mhd_stage_r.cuh"
 #include "mhd_pet.cuh"
+#include "mhd_pet_tma.cuh"

@@ -11,6 +11,40 @@ size_t mhd_work_bytes(const Grid& g)
   return (size_t)(g.ksize > 1 ? W_TOTAL : W2_TOTAL) * (size_t)mhd_padded_cells(g.sv) * sizeof(double);
 }
 
+// 4-D tensor maps (x, y, z, variable) over both time levels, box = 36 x 19 x 1 x {8 | 1} doubles, no swizzle, zero fill
+// outside the array.  The encoder is a driver entry point: looked up at run time, libcuda is not linked.
+bool mhd_make_tensor_maps(Ctx& c)
+{
+  c.umap_ok = false;
+  const Grid& g = c.g;
+  if (c.p.dim != 3 || !c.p.mhd || (g.isize & 1))
+    return false; // global strides must be multiples of 16 bytes
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+      qres != cudaDriverEntryPointSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  const cuuint64_t dims[4] = { (cuuint64_t)g.isize, (cuuint64_t)g.jsize, (cuuint64_t)g.ksize, 8 };
+  const cuuint64_t strides[3] = { (cuuint64_t)g.isize * 8, (cuuint64_t)g.sk * 8, (cuuint64_t)g.sv * 8 };
+  const cuuint32_t estr[4] = { 1, 1, 1, 1 };
+  // the box shape belongs to the map: one variable of one plane per instruction (9 instructions per staged plane)
+  const cuuint32_t box[4] = { (cuuint32_t)PT_RX, (cuuint32_t)PT_RY, 1, 1 };
+  for (int l = 0; l < 2; ++l) {
+    CUresult r = ((EncodeFn)fn)(&c.umap[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, c.U[l], dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+      return false;
+  }
+  c.umap_ok = true;
+  return true;
+}
+
 static MhdArgs make_args(Ctx& c, const double* Uin, double* Uout)
 {
   MhdArgs a;
@@ -89,20 +123,10 @@ static void launch_update_ends(Ctx& c, MhdArgs a)
   }
 }
 
-// stages P+E+T over the whole box (mhd_pet.cuh)
-static cudaError_t launch_pet(Ctx& c, const MhdArgs& a)
+// z-chunking of a z-marching kernel: enough CTAs for whole waves over `slots` resident CTAs, chunks long enough to
+// amortise the 3-plane warm-up
+static int pick_pet_zchunk(int nplanes, long long xy, long long slots)
 {
-  const Grid& g = c.g;
-  if (!c.mhd_pet_attr) {
-    cudaError_t e = cudaFuncSetAttribute(mhd_pet_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PetSmem));
-    if (e != cudaSuccess)
-      return e;
-    c.mhd_pet_attr = true;
-  }
-  dim3 grid((g.isize - 3 + PET_TX - 1) / PET_TX, (g.jsize - 3 + PET_TY - 1) / PET_TY, 1); // cells 2 .. isize-2
-  const int nplanes = g.ksize - 3;                                                      // planes 2 .. ksize-2
-  // enough CTAs for whole waves (2 resident CTAs per SM), chunks long enough to amortise the 3-plane warm-up
-  const long long slots = 2LL * c.sm_count, xy = (long long)grid.x * grid.y;
   int nchunk = 1;
   double best = 1e300;
   for (int n = 1; n <= nplanes; ++n) {
@@ -116,7 +140,44 @@ static cudaError_t launch_pet(Ctx& c, const MhdArgs& a)
       nchunk = n;
     }
   }
-  const int zchunk = (nplanes + nchunk - 1) / nchunk;
+  return (nplanes + nchunk - 1) / nchunk;
+}
+
+// TMA-fed P+E+T kernel (mhd_pet_tma.cuh) when the grid allows it; EK_MHD_PET_TMA=0 forces the plain-load kernel
+static bool use_pet_tma(const Ctx& c)
+{
+  const int v = getenv("EK_MHD_PET_TMA") ? atoi(getenv("EK_MHD_PET_TMA")) : 1;
+  return v != 0 && c.umap_ok;
+}
+
+// stages P+E+T over the whole box
+static cudaError_t launch_pet(Ctx& c, const MhdArgs& a)
+{
+  const Grid& g = c.g;
+  const int nplanes = g.ksize - 3; // planes 2 .. ksize-2
+  if (use_pet_tma(c)) {
+    if (!c.mhd_pet_tma_attr) {
+      cudaError_t e = cudaFuncSetAttribute(mhd_pet_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PetTmaSmem));
+      if (e != cudaSuccess)
+        return e;
+      c.mhd_pet_tma_attr = true;
+    }
+    dim3 grid((g.isize - 3 + PT_TX - 1) / PT_TX, (g.jsize - 3 + PT_TY - 1) / PT_TY, 1); // cells 2 .. isize-2
+    const int zchunk = pick_pet_zchunk(nplanes, (long long)grid.x * grid.y, c.sm_count);
+    grid.z = (nplanes + zchunk - 1) / zchunk;
+    const int level = (a.Uin == c.U[0]) ? 0 : 1;
+    mhd_pet_tma_kernel<<<grid, PT_TX * PT_TY, sizeof(PetTmaSmem), c.stream>>>(a, zchunk, c.umap[level]);
+    c.launches++;
+    return cudaGetLastError();
+  }
+  if (!c.mhd_pet_attr) {
+    cudaError_t e = cudaFuncSetAttribute(mhd_pet_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PetSmem));
+    if (e != cudaSuccess)
+      return e;
+    c.mhd_pet_attr = true;
+  }
+  dim3 grid((g.isize - 3 + PET_TX - 1) / PET_TX, (g.jsize - 3 + PET_TY - 1) / PET_TY, 1);
+  const int zchunk = pick_pet_zchunk(nplanes, (long long)grid.x * grid.y, 2LL * c.sm_count);
   grid.z = (nplanes + zchunk - 1) / zchunk;
   mhd_pet_kernel<0><<<grid, PET_TX * PET_TY, sizeof(PetSmem), c.stream>>>(a, zchunk);
   c.launches++;

@@ -124,6 +124,19 @@ def test_mhd3d_kernel_variants_agree_with_the_oracle(knobs, monkeypatch):
     _check_steps(p, util.random_hydro_state(p, seed=5, mach=2.5), 2)
 
 
+@pytest.mark.parametrize("tma", ["1", "0"])
+@pytest.mark.parametrize("n,bc", [((70, 40, 21), (3, 3, 1, 2, 2, 1)), ((30, 14, 40), (1, 2, 3, 3, 1, 1)), ((32, 16, 5), (3, 3, 3, 3, 3, 3)),
+                                  ((98, 18, 3), (2, 1, 1, 1, 3, 3))])
+def test_mhd3d_tma_fed_predictor_equals_the_plain_load_kernel(n, bc, tma, monkeypatch):
+    """Stages P+E+T fed by TMA box loads (mhd_pet_tma.cuh; grids with an even row length) against the oracle, next to the
+    plain-load kernel on the same states: tiles cut by the domain edge in x and y (zero-filled box parts), z-chunks of
+    one to many planes, every boundary type."""
+    monkeypatch.setenv("EK_MHD_PET_TMA", tma)
+    p = util.make_params(dim=3, mhd=True, n=n, riemann="hlld", bc=bc, smallr=1e-8, smallc=1e-8, box=((0, 1.0), (0, 0.7), (0, 0.4)))
+    assert (p.nx + 2 * p.ghost) % 2 == 0
+    _check_steps(p, util.random_hydro_state(p, seed=11, mach=2.0), 2)
+
+
 @pytest.mark.parametrize("bc", [(3, 3, 3, 3, 3, 3), (1, 1, 1, 1, 1, 1), (2, 2, 1, 3, 3, 2)])
 @pytest.mark.parametrize("layer", ["x", "y", "z", "corner", "none"])
 def test_mhd3d_folded_cfl_reduction_equals_the_standalone_pass(layer, bc, monkeypatch):
