@@ -243,7 +243,7 @@ int ek_comm_attach(ek_ctx* ctx, const void* id, int rank, int nranks, const int3
     const bool want = !(getenv("EK_HALO_OVERLAP") && atoi(getenv("EK_HALO_OVERLAP")) == 0);
     const bool zcopy = c->p.bc[4] == EK_BC_COPY || c->p.bc[5] == EK_BC_COPY;
     const bool xycopy = c->p.bc[0] == EK_BC_COPY || c->p.bc[1] == EK_BC_COPY || c->p.bc[2] == EK_BC_COPY || c->p.bc[3] == EK_BC_COPY;
-    const bool splittable = c->p.mhd ? (c->p.nz >= 2 * c->p.ghost) : hydro_z_splittable(*c);
+    const bool splittable = c->p.mhd ? mhd_z_splittable(*c) : hydro_z_splittable(*c);
     double ok = (want && c->p.dim == 3 && zcopy && !xycopy && splittable) ? 1.0 : 0.0;
     if (nranks > 1) {
       if (cudaMemcpyAsync(c->scratch, &ok, sizeof(double), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { c->err = "overlap probe: H2D failed"; return EK_ERR_CUDA; }

@@ -47,6 +47,7 @@ struct Ctx {
   alignas(64) CUtensorMap umap[2];
   bool umap_ok = false;
   bool mhd_pet_tma_attr = false;
+  const void* mhd_ru_attr_for = nullptr; // fused R+U kernel instance whose dynamic shared-memory limit has been raised
   // communicator (z-slab / cartesian neighbours)
   void* nccl_comm = nullptr;
   int rank = 0, nranks = 1;
@@ -80,6 +81,7 @@ cudaError_t launch_mhd_step(Ctx& c, const double* Uin, double* Uout, int part = 
 cudaError_t launch_mhd_invdt(Ctx& c, const double* U);
 cudaError_t launch_mhd_invdt_layers(Ctx& c, const double* U);
 bool mhd_dt_folded(const Ctx& c);
+bool mhd_z_splittable(const Ctx& c); // the update can be cut into end planes / chunks first, the rest after
 size_t mhd_work_bytes(const Grid& g);
 bool mhd_make_tensor_maps(Ctx& c); // false: TMA path unavailable for this grid / driver (the plain-load kernel serves it)
 // ek_comm.cu

@@ -337,6 +337,10 @@ EK_HD void mhd_trace_load(const Grid& g, const double* __restrict__ U, const Mhd
   f.Czp = active ? UC[sk] : 0.0;
 }
 
+// store of one value of the compact state S.  (Measured: a streaming / evict-first store, __stcs, does not keep the
+// planes of U in L2 for the neighbouring CTAs -- DRAM reads unchanged at 16 GB -- and costs 0.7 ms per step.)
+EK_HD void st_s(double* p, double v) { *p = v; }
+
 // Sc: tile pointer of the cell's compact state (output)
 template <class IN>
 EK_HD void mhd_trace_core(const Grid& g, const MhdTraceB& fb, const IN& P, double* __restrict__ Sc, double dtdx,
@@ -350,21 +354,21 @@ EK_HD void mhd_trace_core(const Grid& g, const MhdTraceB& fb, const IN& P, doubl
   // face-centred half step: AL + sAL0 etc. (:872-877, :889-894) and halved transverse slopes (:810-822)
   if (in_j && in_k) {
     const double GLR = P.ej(2), FLR = P.ek(1);
-    Sc[TL * SFA] = AL + (+(GLR - GLL) * dtdy * 0.5 - (FLR - FLL) * dtdz * 0.5);
-    Sc[TL * SDAY] = mhd_half_slope(0.5 * xst, g.slope_k, fb.Aym, AL, fb.Ayp);
-    Sc[TL * SDAZ] = mhd_half_slope(0.5 * xst, g.slope_k, fb.Azm, AL, fb.Azp);
+    st_s(Sc + TL * SFA, AL + (+(GLR - GLL) * dtdy * 0.5 - (FLR - FLL) * dtdz * 0.5));
+    st_s(Sc + TL * SDAY, mhd_half_slope(0.5 * xst, g.slope_k, fb.Aym, AL, fb.Ayp));
+    st_s(Sc + TL * SDAZ, mhd_half_slope(0.5 * xst, g.slope_k, fb.Azm, AL, fb.Azp));
   }
   if (in_i && in_k) {
     const double GRL = P.ei(2), ELR = P.ek(0);
-    Sc[TL * SFB] = BL + (-(GRL - GLL) * dtdx * 0.5 + (ELR - ELL) * dtdz * 0.5);
-    Sc[TL * SDBX] = mhd_half_slope(0.5 * xst, g.slope_k, fb.Bxm, BL, fb.Bxp);
-    Sc[TL * SDBZ] = mhd_half_slope(0.5 * xst, g.slope_k, fb.Bzm, BL, fb.Bzp);
+    st_s(Sc + TL * SFB, BL + (-(GRL - GLL) * dtdx * 0.5 + (ELR - ELL) * dtdz * 0.5));
+    st_s(Sc + TL * SDBX, mhd_half_slope(0.5 * xst, g.slope_k, fb.Bxm, BL, fb.Bxp));
+    st_s(Sc + TL * SDBZ, mhd_half_slope(0.5 * xst, g.slope_k, fb.Bzm, BL, fb.Bzp));
   }
   if (in_i && in_j) {
     const double FRL = P.ei(1), ERL = P.ej(0);
-    Sc[TL * SFC] = CL + (+(FRL - FLL) * dtdx * 0.5 - (ERL - ELL) * dtdy * 0.5);
-    Sc[TL * SDCX] = mhd_half_slope(0.5 * xst, g.slope_k, fb.Cxm, CL, fb.Cxp);
-    Sc[TL * SDCY] = mhd_half_slope(0.5 * xst, g.slope_k, fb.Cym, CL, fb.Cyp);
+    st_s(Sc + TL * SFC, CL + (+(FRL - FLL) * dtdx * 0.5 - (ERL - ELL) * dtdy * 0.5));
+    st_s(Sc + TL * SDCX, mhd_half_slope(0.5 * xst, g.slope_k, fb.Cxm, CL, fb.Cxp));
+    st_s(Sc + TL * SDCY, mhd_half_slope(0.5 * xst, g.slope_k, fb.Cym, CL, fb.Cyp));
   }
   if (!(in_i && in_j && in_k))
     return;
@@ -396,8 +400,8 @@ EK_HD void mhd_trace_core(const Grid& g, const MhdTraceB& fb, const IN& P, doubl
     sp0 = (-u * dpx - dux * gp) * dtdx;
     sB0 = (v * dAx + A * dvx - u * dBx - B * dux) * dtdx;
     sC0 = (w * dAx + A * dwx - u * dCx - C * dux) * dtdx;
-    Sc[TL * (SX + 0)] = drx; Sc[TL * (SX + 1)] = dpx; Sc[TL * (SX + 2)] = dux; Sc[TL * (SX + 3)] = dvx; Sc[TL * (SX + 4)] = dwx;
-    Sc[TL * (SX + 5)] = dBx; Sc[TL * (SX + 6)] = dCx;
+    st_s(Sc + TL * (SX + 0), drx); st_s(Sc + TL * (SX + 1), dpx); st_s(Sc + TL * (SX + 2), dux); st_s(Sc + TL * (SX + 3), dvx); st_s(Sc + TL * (SX + 4), dwx);
+    st_s(Sc + TL * (SX + 5), dBx); st_s(Sc + TL * (SX + 6), dCx);
   }
   {
     double d[8];
@@ -413,8 +417,8 @@ EK_HD void mhd_trace_core(const Grid& g, const MhdTraceB& fb, const IN& P, doubl
     sp0 += (-v * dpy - dvy * gp) * dtdy;
     sA0 = (u * dBy + B * duy - v * dAy - A * dvy) * dtdy;
     sC0 += (w * dBy + B * dwy - v * dCy - C * dvy) * dtdy;
-    Sc[TL * (SY + 0)] = dry; Sc[TL * (SY + 1)] = dpy; Sc[TL * (SY + 2)] = duy; Sc[TL * (SY + 3)] = dvy; Sc[TL * (SY + 4)] = dwy;
-    Sc[TL * (SY + 5)] = dAy; Sc[TL * (SY + 6)] = dCy;
+    st_s(Sc + TL * (SY + 0), dry); st_s(Sc + TL * (SY + 1), dpy); st_s(Sc + TL * (SY + 2), duy); st_s(Sc + TL * (SY + 3), dvy); st_s(Sc + TL * (SY + 4), dwy);
+    st_s(Sc + TL * (SY + 5), dAy); st_s(Sc + TL * (SY + 6), dCy);
   }
   {
     double d[8];
@@ -430,17 +434,17 @@ EK_HD void mhd_trace_core(const Grid& g, const MhdTraceB& fb, const IN& P, doubl
     sp0 += (-w * dpz - dwz * gp) * dtdz;
     sA0 += (u * dCz + C * duz - w * dAz - A * dwz) * dtdz;
     sB0 += (v * dCz + C * dvz - w * dBz - B * dwz) * dtdz;
-    Sc[TL * (SZ + 0)] = drz; Sc[TL * (SZ + 1)] = dpz; Sc[TL * (SZ + 2)] = duz; Sc[TL * (SZ + 3)] = dvz; Sc[TL * (SZ + 4)] = dwz;
-    Sc[TL * (SZ + 5)] = dAz; Sc[TL * (SZ + 6)] = dBz;
+    st_s(Sc + TL * (SZ + 0), drz); st_s(Sc + TL * (SZ + 1), dpz); st_s(Sc + TL * (SZ + 2), duz); st_s(Sc + TL * (SZ + 3), dvz); st_s(Sc + TL * (SZ + 4), dwz);
+    st_s(Sc + TL * (SZ + 5), dAz); st_s(Sc + TL * (SZ + 6), dBz);
   }
-  Sc[TL * (SC + ID)] = r + sr0;
-  Sc[TL * (SC + IP)] = p + sp0;
-  Sc[TL * (SC + IU)] = u + su0;
-  Sc[TL * (SC + IV)] = v + sv0;
-  Sc[TL * (SC + IW)] = w + sw0;
-  Sc[TL * (SC + IA)] = A + sA0;
-  Sc[TL * (SC + IB)] = B + sB0;
-  Sc[TL * (SC + IC)] = C + sC0;
+  st_s(Sc + TL * (SC + ID), r + sr0);
+  st_s(Sc + TL * (SC + IP), p + sp0);
+  st_s(Sc + TL * (SC + IU), u + su0);
+  st_s(Sc + TL * (SC + IV), v + sv0);
+  st_s(Sc + TL * (SC + IW), w + sw0);
+  st_s(Sc + TL * (SC + IA), A + sA0);
+  st_s(Sc + TL * (SC + IB), B + sB0);
+  st_s(Sc + TL * (SC + IC), C + sC0);
 }
 
 EK_HD void mhd_trace_core(const Grid& g, const double* __restrict__ U, const MhdTraceIn& P, double* __restrict__ Sc, double dtdx,
@@ -639,47 +643,60 @@ EK_HD void mhd_stage_emfs(const Grid& g, const double* __restrict__ S, double* _
 // update is repeated here (same expression, same operand order: the value is the one the neighbour stores).  Cells of
 // the last interior layer along x, y or z return 0: their upper faces are ghosts, set by the boundary fill / halo
 // exchange that follows the step (mhd_invdt_layers_kernel takes those cells afterwards).
-template <bool WANT_INVDT>
-EK_HD double mhd_stage_update_t(const Grid& g, const double* __restrict__ Uin, const double* __restrict__ F,
-                                const double* __restrict__ EMF, double* __restrict__ Uout, double dtdx, double dtdy, double dtdz,
-                                const MhdIdx& x)
+//
+// Where the fluxes and EMFs come from is a template parameter SRC: flux component v (0..4) of the cell's own lower
+// x / y / z face and of the lower face of its +x / +y / +z neighbour, EMF component c (0 = x, 1 = y, 2 = z) at the
+// lower edges of the cell and of its +x, +y, +z, +x+y, +x+z, +y+z neighbours.  MhdUpdGlobal reads the F / EMF work
+// arrays (stage U as a kernel of its own); the fused R+U kernel reads its shared-memory planes (mhd_ru.cuh).
+struct MhdUpdGlobal {
+  const double *F0, *Fi, *Fj, *Fk;           // tile pointers of the flux array at c, c+1, c+sj, c+sk
+  const double *E0, *Ei, *Ej, *Ek, *Eij, *Eik, *Ejk; // ... of the EMF array
+  EK_HD double fx0(int v) const { return F0[TL * v]; }
+  EK_HD double fy0(int v) const { return F0[TL * (5 + v)]; }
+  EK_HD double fz0(int v) const { return F0[TL * (10 + v)]; }
+  EK_HD double fxi(int v) const { return Fi[TL * v]; }
+  EK_HD double fyj(int v) const { return Fj[TL * (5 + v)]; }
+  EK_HD double fzk(int v) const { return Fk[TL * (10 + v)]; }
+  EK_HD double e0(int c) const { return E0[TL * c]; }
+  EK_HD double ei(int c) const { return Ei[TL * c]; }
+  EK_HD double ej(int c) const { return Ej[TL * c]; }
+  EK_HD double ek(int c) const { return Ek[TL * c]; }
+  EK_HD double eij(int c) const { return Eij[TL * c]; }
+  EK_HD double eik(int c) const { return Eik[TL * c]; }
+  EK_HD double ejk(int c) const { return Ejk[TL * c]; }
+};
+
+// x: an INTERIOR cell (checked by the caller)
+template <bool WANT_INVDT, class SRC>
+EK_HD double mhd_update_core(const Grid& g, const double* __restrict__ Uin, double* __restrict__ Uout, const SRC& P, double dtdx,
+                             double dtdy, double dtdz, const MhdIdx& x)
 {
   const int gw = g.gw;
-  if (x.i < gw || x.j < gw || x.k < gw || x.i >= g.isize - gw || x.j >= g.jsize - gw || x.k >= g.ksize - gw)
-    return 0.0;
   const unsigned c = x.c;
   const long long sv = g.sv;
-  const double* __restrict__ F0 = F + tile_off<15>(c);
-  const double* __restrict__ Fi = F + tile_off<15>(c + 1);
-  const double* __restrict__ Fj = F + tile_off<15>(c + x.sj);
-  const double* __restrict__ Fk = F + tile_off<15>(c + x.sk);
   const double* __restrict__ Uc = Uin + c;
   double* __restrict__ Oc = Uout + c;
   double un[8];
 #pragma unroll
   for (int v = 0; v < 5; ++v) {
     double u = Uc[sv * v];
-    u += F0[TL * v] * dtdx;
-    u -= Fi[TL * v] * dtdx;
-    u += F0[TL * (5 + v)] * dtdy;
-    u -= Fj[TL * (5 + v)] * dtdy;
-    u += F0[TL * (10 + v)] * dtdz;
-    u -= Fk[TL * (10 + v)] * dtdz;
+    u += P.fx0(v) * dtdx;
+    u -= P.fxi(v) * dtdx;
+    u += P.fy0(v) * dtdy;
+    u -= P.fyj(v) * dtdy;
+    u += P.fz0(v) * dtdz;
+    u -= P.fzk(v) * dtdz;
     Oc[sv * v] = u;
     un[v] = u;
   }
-  const double* __restrict__ E0 = EMF + tile_off<3>(c);
-  const double* __restrict__ Ei = EMF + tile_off<3>(c + 1);
-  const double* __restrict__ Ej = EMF + tile_off<3>(c + x.sj);
-  const double* __restrict__ Ek = EMF + tile_off<3>(c + x.sk);
   double A = Uc[sv * IA], B = Uc[sv * IB], C = Uc[sv * IC];
-  const double ex = E0[0], ey = E0[TL], ez = E0[2 * TL];
-  A += (Ej[2 * TL] - ez) * dtdy;
-  B -= (Ei[2 * TL] - ez) * dtdx;
-  A -= (Ek[TL] - ey) * dtdz;
-  B += (Ek[0] - ex) * dtdz;
-  C += (Ei[TL] - ey) * dtdx;
-  C -= (Ej[0] - ex) * dtdy;
+  const double ex = P.e0(0), ey = P.e0(1), ez = P.e0(2);
+  A += (P.ej(2) - ez) * dtdy;
+  B -= (P.ei(2) - ez) * dtdx;
+  A -= (P.ek(1) - ey) * dtdz;
+  B += (P.ek(0) - ex) * dtdz;
+  C += (P.ei(1) - ey) * dtdx;
+  C -= (P.ej(0) - ex) * dtdy;
   Oc[sv * IA] = A;
   Oc[sv * IB] = B;
   Oc[sv * IC] = C;
@@ -690,30 +707,42 @@ EK_HD double mhd_stage_update_t(const Grid& g, const double* __restrict__ Uin, c
   // the new field on the three upper faces = lower faces of the +x / +y / +z neighbours
   const unsigned sj = x.sj, sk = x.sk;
   double A1 = Uc[sv * IA + 1], B1 = Uc[sv * IB + sj], C1 = Uc[sv * IC + sk];
-  {
-    const double* __restrict__ Ejn = EMF + tile_off<3>(c + 1 + sj);
-    const double* __restrict__ Ekn = EMF + tile_off<3>(c + 1 + sk);
-    A1 += (Ejn[2 * TL] - Ei[2 * TL]) * dtdy;
-    A1 -= (Ekn[TL] - Ei[TL]) * dtdz;
-  }
-  {
-    const double* __restrict__ Ein = EMF + tile_off<3>(c + sj + 1);
-    const double* __restrict__ Ekn = EMF + tile_off<3>(c + sj + sk);
-    B1 -= (Ein[2 * TL] - Ej[2 * TL]) * dtdx;
-    B1 += (Ekn[0] - Ej[0]) * dtdz;
-  }
-  {
-    const double* __restrict__ Ein = EMF + tile_off<3>(c + sk + 1);
-    const double* __restrict__ Ejn = EMF + tile_off<3>(c + sk + sj);
-    C1 += (Ein[TL] - Ek[TL]) * dtdx;
-    C1 -= (Ejn[0] - Ek[0]) * dtdy;
-  }
+  A1 += (P.eij(2) - P.ei(2)) * dtdy;
+  A1 -= (P.eik(1) - P.ei(1)) * dtdz;
+  B1 -= (P.eij(2) - P.ej(2)) * dtdx;
+  B1 += (P.ejk(0) - P.ej(0)) * dtdz;
+  C1 += (P.eik(1) - P.ek(1)) * dtdx;
+  C1 -= (P.ejk(0) - P.ek(0)) * dtdy;
   un[IA] = A;
   un[IB] = B;
   un[IC] = C;
   double q[8];
   mhd_cons_to_prim(g, un, A1, B1, C1, q);
   return mhd_cell_invdt(g, q);
+}
+
+template <bool WANT_INVDT>
+EK_HD double mhd_stage_update_t(const Grid& g, const double* __restrict__ Uin, const double* __restrict__ F,
+                                const double* __restrict__ EMF, double* __restrict__ Uout, double dtdx, double dtdy, double dtdz,
+                                const MhdIdx& x)
+{
+  const int gw = g.gw;
+  if (x.i < gw || x.j < gw || x.k < gw || x.i >= g.isize - gw || x.j >= g.jsize - gw || x.k >= g.ksize - gw)
+    return 0.0;
+  const unsigned c = x.c;
+  MhdUpdGlobal P;
+  P.F0 = F + tile_off<15>(c);
+  P.Fi = F + tile_off<15>(c + 1);
+  P.Fj = F + tile_off<15>(c + x.sj);
+  P.Fk = F + tile_off<15>(c + x.sk);
+  P.E0 = EMF + tile_off<3>(c);
+  P.Ei = EMF + tile_off<3>(c + 1);
+  P.Ej = EMF + tile_off<3>(c + x.sj);
+  P.Ek = EMF + tile_off<3>(c + x.sk);
+  P.Eij = EMF + tile_off<3>(c + 1 + x.sj);
+  P.Eik = EMF + tile_off<3>(c + 1 + x.sk);
+  P.Ejk = EMF + tile_off<3>(c + x.sj + x.sk);
+  return mhd_update_core<WANT_INVDT>(g, Uin, Uout, P, dtdx, dtdy, dtdz, x);
 }
 
 EK_HD void mhd_stage_update(const Grid& g, const double* __restrict__ Uin, const double* __restrict__ F, const double* __restrict__ EMF,

@@ -229,5 +229,6 @@ __global__ void __launch_bounds__(256) mhd2d_update_kernel(const MhdArgs a)
 } // namespace ek
 
 #include "mhd_stage_r.cuh"
+#include "mhd_ru.cuh"
 #include "mhd_pet.cuh"
 #include "mhd_pet_tma.cuh"

@@ -184,12 +184,111 @@ static cudaError_t launch_pet(Ctx& c, const MhdArgs& a)
   return cudaGetLastError();
 }
 
-// One 3-D step = P+E+T -> S, R -> F / EMF, U.
-// part: 0 = the whole step; 1 = every stage, but the update only on the END planes; 2 = the update of the MIDDLE planes
+// ---- fused R+U kernel (mhd_ru.cuh): z-chunking ----------------------------------------------------------------------
+// one CTA per SM; a chunk of zc planes solves zc+1 (the Riemann problems of the plane above its last one)
+struct RuPlan {
+  int zchunk, nchunk;
+  bool splittable; // >= 3 chunks whose end chunks hold the gw planes the z neighbours need
+};
+static int ru_pick_zchunk(int nz, long long xy, int sm_count, int min_chunks, int min_len)
+{
+  int best = nz;
+  double best_cost = 1e300;
+  for (int n = min_chunks; n <= nz; ++n) {
+    const int zc = (nz + n - 1) / n;
+    if (zc < min_len && n > min_chunks)
+      break;
+    const long long ctas = xy * ((nz + zc - 1) / zc);
+    const long long waves = (ctas + sm_count - 1) / sm_count;
+    const double cost = (double)(waves * sm_count) / (double)ctas * (zc + 1.0) / zc;
+    if (cost < best_cost - 1e-12) {
+      best_cost = cost;
+      best = zc;
+    }
+  }
+  return best;
+}
+static RuPlan ru_plan(const Ctx& c, bool want_split)
+{
+  const Grid& g = c.g;
+  const long long xy = (long long)((g.nx + RU_TX - 2) / (RU_TX - 1)) * ((g.ny + RU_TY - 2) / (RU_TY - 1));
+  RuPlan z;
+  z.zchunk = ru_pick_zchunk(g.nz, xy, c.sm_count, 1, 8);
+  z.nchunk = (g.nz + z.zchunk - 1) / z.zchunk;
+  z.splittable = false;
+  if (!want_split)
+    return z;
+  const int zc = (z.nchunk >= 3) ? z.zchunk : ru_pick_zchunk(g.nz, xy, c.sm_count, 3, g.gw);
+  const int nc = (g.nz + zc - 1) / zc;
+  const int last = g.nz - (nc - 1) * zc;
+  if (nc >= 3 && zc >= g.gw && last >= g.gw) {
+    z.zchunk = zc;
+    z.nchunk = nc;
+    z.splittable = true;
+  }
+  return z;
+}
+
+// EK_MHD_RU=1 selects the fused R+U kernel.  Default: the two-kernel form (stage R -> F / EMF arrays -> stage U).
+// Measured at 512^3 (profiles/r02_mhd_ru_ncu.txt): fused 50.1 ms against 28.6 + 7.8 ms.  Its 147 KB of shared-memory
+// planes leave stage R's ~290 loads per thread a third of the L1 they have in the flat kernel (L1 hit rate 41 % -> 22 %,
+// long-scoreboard stalls 1.8 -> 3.9 per issue, DRAM reads 44 -> 59 GB): what the fusion saves in F / EMF traffic (48 GB)
+// it loses several times over in latency of the reconstruction loads.
+static bool use_ru(const Ctx& c)
+{
+  const int v = getenv("EK_MHD_RU") ? atoi(getenv("EK_MHD_RU")) : 0;
+  return v != 0 && c.p.dim == 3;
+}
+bool mhd_z_splittable(const Ctx& c) { return use_ru(c) ? ru_plan(c, true).splittable : (c.p.nz >= 2 * c.p.ghost); }
+
+// part: 0 = every chunk, 1 = the two end chunks, 2 = the middle chunks
+template <int RS>
+static cudaError_t launch_ru(Ctx& c, const MhdArgs& a, int part)
+{
+  const bool fold = mhd_dt_folded(c);
+  void (*kern)(const MhdRuArgs) = fold ? mhd_ru_kernel<RS, true> : mhd_ru_kernel<RS, false>;
+  if (c.mhd_ru_attr_for != (const void*)kern) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RuSmem));
+    if (e != cudaSuccess)
+      return e;
+    c.mhd_ru_attr_for = (const void*)kern;
+  }
+  const Grid& g = c.g;
+  const RuPlan z = ru_plan(c, part != 0);
+  if (part != 0 && !z.splittable)
+    return cudaErrorInvalidValue;
+  MhdRuArgs ra;
+  ra.a = a;
+  ra.zchunk = z.zchunk;
+  ra.zfirst = 0;
+  ra.zstep = 1;
+  dim3 grid((g.nx + RU_TX - 2) / (RU_TX - 1), (g.ny + RU_TY - 2) / (RU_TY - 1), z.nchunk);
+  if (part == 1) {
+    ra.zstep = z.nchunk - 1;
+    grid.z = 2;
+  } else if (part == 2) {
+    ra.zfirst = 1;
+    grid.z = z.nchunk - 2;
+  }
+  kern<<<grid, dim3(RU_TX, RU_TY, 1), sizeof(RuSmem), c.stream>>>(ra);
+  c.launches++;
+  return cudaGetLastError();
+}
+
+// One 3-D step = P+E+T -> S, then R+U fused (or R -> F / EMF arrays, then U).
+// part: 0 = the whole step; 1 = every stage, but the update only on the END planes (chunks); 2 = the update of the rest
 template <int RS>
 static cudaError_t launch_step(Ctx& c, const double* Uin, double* Uout, int part)
 {
   const MhdArgs a = make_args(c, Uin, Uout);
+  if (use_ru(c)) {
+    if (part != 2) {
+      cudaError_t e = launch_pet(c, a);
+      if (e != cudaSuccess)
+        return e;
+    }
+    return launch_ru<RS>(c, a, part);
+  }
   if (part == 2) {
     MhdArgs m = a;
     m.upd_klo = 2 * c.g.gw;

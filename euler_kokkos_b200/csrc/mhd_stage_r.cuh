@@ -18,9 +18,11 @@ struct FaceProblem {
 
 #define STG_SOLVER __device__ __noinline__
 
-// solve and store the flux through a lower face; Fn/Ft1/Ft2: where the normal / transverse momentum fluxes go
+// solve and store the flux through a lower face: mass at Fd[0], energy at Fd[oe], normal / transverse momentum fluxes
+// at Fd[on], Fd[ot1], Fd[ot2] (the caller knows the layout: AoSoA tile of the F work array, or a shared-memory plane)
 template <int RS>
-STG_SOLVER void stg_face_solver(double gamma0, double entho, MhdSide L, MhdSide R, double a, double* __restrict__ Fd, int on, int ot1, int ot2)
+STG_SOLVER void stg_face_solver(double gamma0, double entho, MhdSide L, MhdSide R, double a, double* __restrict__ Fd, int oe, int on, int ot1,
+                                int ot2)
 {
   Grid g{};
   g.gamma0 = gamma0;
@@ -28,7 +30,7 @@ STG_SOLVER void stg_face_solver(double gamma0, double entho, MhdSide L, MhdSide 
   double f[5];
   mhd_riemann<RS>(g, L, R, a, f);
   Fd[0] = f[0];
-  Fd[TL] = f[1];
+  Fd[oe] = f[1];
   Fd[on] = f[2];
   Fd[ot1] = f[3];
   Fd[ot2] = f[4];
@@ -49,7 +51,7 @@ __device__ __forceinline__ void stg_solve_face(const Grid& g, const FaceProblem&
   constexpr int on = (D == 0) ? 2 : (D == 1) ? 3 : 4;  // normal momentum = mom_D
   constexpr int ot1 = (D == 0) ? 3 : (D == 1) ? 2 : 3; // first transverse: y, x, y
   constexpr int ot2 = (D == 0) ? 4 : (D == 1) ? 4 : 2; // second transverse: z, z, x
-  stg_face_solver<RS>(g.gamma0, g.entho, p.L, p.R, p.a, Fc + TL * 5 * D, TL * on, TL * ot1, TL * ot2);
+  stg_face_solver<RS>(g.gamma0, g.entho, p.L, p.R, p.a, Fc + TL * 5 * D, TL, TL * on, TL * ot1, TL * ot2);
 }
 
 // ---- the kernel: plain loads, reconstruction, solver calls ---------------------------------------------------------

@@ -112,9 +112,10 @@ def test_mhd3d_divb_and_conservation():
     assert d0 < 1e-11 and d1 < 1e-11, (d0, d1)
 
 
-@pytest.mark.parametrize("knobs", [{"EK_MHD_YCHUNK": "0"}, {"EK_MHD_YCHUNK": "5"}, {"EK_MHD_YCHUNK": "16"}, {"EK_MHD_DTFOLD": "0"}])
+@pytest.mark.parametrize("knobs", [{"EK_MHD_RU": "0", "EK_MHD_YCHUNK": "0"}, {"EK_MHD_RU": "0", "EK_MHD_YCHUNK": "5"}, {"EK_MHD_RU": "0"},
+                                   {"EK_MHD_RU": "0", "EK_MHD_DTFOLD": "0"}, {"EK_MHD_RU": "1"}, {"EK_MHD_RU": "1", "EK_MHD_DTFOLD": "0"}])
 def test_mhd3d_kernel_variants_agree_with_the_oracle(knobs, monkeypatch):
-    """the launch orders of stage R / U (flat, y-chunked) and both placements of the CFL reduction are held to the same
+    """the fused R+U kernel and the two-kernel form (with its launch orders: flat, y-chunked) and both placements of the CFL reduction are held to the same
     one-step tolerance (the variants that lost in round 1 -- cp.async-staged and fully inlined stage R, z-grouped order,
     L2 prefetches, three-kernel P/E/T, the slab-pipelined launch -- are gone; DESIGN.md keeps their measurements)"""
     for k, v in knobs.items():
@@ -122,6 +123,18 @@ def test_mhd3d_kernel_variants_agree_with_the_oracle(knobs, monkeypatch):
     p = util.make_params(dim=3, mhd=True, n=(45, 26, 19), riemann="hlld", bc=(3, 3, 1, 2, 2, 1), smallr=1e-8, smallc=1e-8,
                          box=((0, 1.0), (0, 0.8), (0, 0.5)))
     _check_steps(p, util.random_hydro_state(p, seed=5, mach=2.5), 2)
+
+
+@pytest.mark.parametrize("ru", ["1", "0"])
+@pytest.mark.parametrize("n,bc", [((31, 15, 9), (3, 3, 1, 2, 2, 1)), ((62, 30, 4), (1, 2, 3, 3, 1, 1)), ((63, 31, 17), (3, 3, 3, 3, 3, 3)),
+                                  ((33, 46, 3), (2, 1, 1, 1, 3, 3)), ((96, 20, 26), (1, 1, 1, 1, 1, 1))])
+def test_mhd3d_fused_flux_update_kernel(n, bc, ru, monkeypatch):
+    """Stages R+U fused (mhd_ru.cuh: 31 x 15 tiles + halo lane / row, z-march) against the oracle, next to the two-kernel
+    form on the same states: grids that are exact multiples of the tile, one cell more, one less; short and long z-chunks;
+    every boundary type."""
+    monkeypatch.setenv("EK_MHD_RU", ru)
+    p = util.make_params(dim=3, mhd=True, n=n, riemann="hlld", bc=bc, smallr=1e-8, smallc=1e-8, box=((0, 1.0), (0, 0.7), (0, 0.4)))
+    _check_steps(p, util.random_hydro_state(p, seed=13, mach=2.0), 2)
 
 
 @pytest.mark.parametrize("tma", ["1", "0"])
