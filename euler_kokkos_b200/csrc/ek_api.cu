@@ -239,6 +239,7 @@ static int fill_boundaries(Ctx& c, double* U)
   }
   if (c.halo_ready_for == U)
     c.halo_ready_for = nullptr; // consumed
+  c.ghosts_valid_for = U;
   return EK_OK;
 }
 
@@ -284,8 +285,9 @@ static int enqueue_step(Ctx& c, int use_host_dt, double host_dt, int max_steps)
   double* Uin = c.U[c.cur];
   double* Uout = c.U[1 - c.cur];
   if (c.p.mhd) {
-    // MHD: boundaries -> (prims) -> dt -> step   (SolverMHDMuscl.cpp:463-513)
-    int rc = fill_boundaries(c, Uin);
+    // MHD: boundaries -> (prims) -> dt -> step   (SolverMHDMuscl.cpp:463-513).  The host-driven loop calls
+    // ek_compute_dt first, which has just filled and exchanged the ghosts of this level: not repeated (idempotent anyway)
+    int rc = (c.ghosts_valid_for == Uin) ? EK_OK : fill_boundaries(c, Uin);
     if (rc != EK_OK)
       return rc;
     if (!use_host_dt) {
@@ -353,6 +355,7 @@ static int enqueue_step(Ctx& c, int use_host_dt, double host_dt, int max_steps)
       return rc;
     c.dt_primed = true;
   }
+  c.ghosts_valid_for = nullptr; // the new level's ghosts are not filled yet
   post_step_kernel<<<1, 1, 0, c.stream>>>(c.ts, max_steps);
   c.launches++;
   EK_CUDA(&c, cudaGetLastError());
@@ -520,6 +523,7 @@ int ek_upload_state(ek_ctx* ctx, const double* U_host)
   c->mhd_prims_of = nullptr;
   c->mhd_dt_partial_for = nullptr;
   c->halo_ready_for = nullptr;
+  c->ghosts_valid_for = nullptr;
   EK_CUDA(c, cudaStreamSynchronize(c->stream)); // the host buffer may be pageable / reused
   return EK_OK;
 }
@@ -540,6 +544,7 @@ int ek_device_state(ek_ctx* ctx, double** dptr)
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
   *dptr = c->U[c->cur];
   c->dt_primed = false; // the caller may modify the state through this pointer
+  c->ghosts_valid_for = nullptr;
   c->mhd_prims_of = nullptr;
   c->mhd_dt_partial_for = nullptr;
   c->halo_ready_for = nullptr;

@@ -25,6 +25,7 @@ struct Ctx {
   // level `halo_ready_for` have already been exchanged (on comm_stream, completion = ev_halo)
   bool overlap_ok = false;              // decided at ek_comm_attach, identical on every rank
   const double* halo_ready_for = nullptr;
+  const double* ghosts_valid_for = nullptr; // level whose ghost cells are filled and exchanged (nothing has written it since)
   double* U[2] = { nullptr, nullptr }; // ping-pong levels
   int cur = 0;                         // index of the current level
   double* grav = nullptr;

@@ -90,8 +90,11 @@ __device__ __forceinline__ void mhd_block_max_invdt(double m, TimeState* ts)
 
 // stage U.  INVDT: the CFL reduction of the NEXT step rides along (every interior cell except the last layer along
 // x, y, z, see mhd_stage_update_t); pre_step_kernel has zeroed ts->invdt_bits before the step's kernels run.
+#ifndef EK_MHD_U_MINB
+#define EK_MHD_U_MINB 5 // resident CTAs of 256 threads the register budget is cut for (measured: 4 and 6 are slower)
+#endif
 template <bool INVDT>
-__global__ void __launch_bounds__(256, 5) mhd_update_kernel(const MhdArgs a)
+__global__ void __launch_bounds__(256, EK_MHD_U_MINB) mhd_update_kernel(const MhdArgs a)
 {
   if (a.ts->finished)
     return;

@@ -147,7 +147,7 @@ class Case:
 
     def kernel_name(self) -> str:
         if self.params.mhd:
-            return ("mhd step kernels (mhd_pet + mhd_faces_edges_call + mhd_update)" if self.params.dim == 3
+            return ("mhd step kernels (mhd_pet_tma + mhd_faces_edges_call + mhd_update)" if self.params.dim == 3
                     else "mhd2d step kernels (prims + elec + trace + faces_edge + update)")
         return f"hydro_step_kernel<{self.params.dim}>"
 
