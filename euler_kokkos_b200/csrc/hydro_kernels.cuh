@@ -27,16 +27,19 @@ template <int DIM, int TY>
 struct HydroSmem {
   static constexpr int NV = HydroTraits<DIM>::NV;
   static constexpr int ROWS = TY + 4;
-  static constexpr int PLANE = ROWS * 32; // doubles per variable
+  static constexpr int PLANE = ROWS * 32; // doubles per variable of the primitive ring (tile + 2-cell halo)
+  // face states, fluxes and the running update only ever exist for rows 1 .. TY+2 (the cells that are traced):
+  // their planes are two rows shorter and indexed with the row offset by one (so2 = so - 32)
+  static constexpr int PLANE2 = (TY + 2) * 32;
   static constexpr int NRING = (DIM == 3) ? 3 : 1;
-  double q[NRING][NV * PLANE];       // primitives: ring of planes
-  double mx[NV * PLANE];             // state on the XMAX face of each cell (left state of face i+1)
-  double my[NV * PLANE];             // state on the YMAX face of each cell
-  double fx[NV * PLANE];             // flux*dt/dx through the lower x face of each cell
-  double fy[NV * PLANE];             // flux*dt/dy through the lower y face of each cell
-  double mz[(DIM == 3) ? 2 : 1][NV * PLANE]; // ZMAX-face state, double buffered by plane parity (3-D)
-  double part[1][NV * PLANE];                // partial update of the previous plane (3-D)
-  double red[ROWS];                  // per-warp invDt maxima
+  double q[NRING][NV * PLANE];        // primitives: ring of planes
+  double mx[NV * PLANE2];             // state on the XMAX face of each cell (left state of face i+1)
+  double my[NV * PLANE2];             // state on the YMAX face of each cell
+  double fx[NV * PLANE2];             // flux*dt/dx through the lower x face of each cell
+  double fy[NV * PLANE2];             // flux*dt/dy through the lower y face of each cell
+  double mz[(DIM == 3) ? 2 : 1][NV * PLANE2]; // ZMAX-face state, double buffered by plane parity (3-D)
+  double part[1][NV * PLANE2];                // partial update of the previous plane (3-D)
+  double red[ROWS];                   // per-warp invDt maxima
 };
 
 struct HydroArgs {
@@ -62,7 +65,7 @@ __global__ void __launch_bounds__(32 * (TY + 4 - 2 * FOLD), 1) hydro_step_kernel
   static_assert(FOLD == 0 || DIM == 3, "folded halo rows: 3-D only");
   constexpr int NV = HydroTraits<DIM>::NV;
   using Smem = HydroSmem<DIM, TY>;
-  constexpr int PLANE = Smem::PLANE;
+  constexpr int PLANE = Smem::PLANE, PLANE2 = Smem::PLANE2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
 
@@ -75,7 +78,8 @@ __global__ void __launch_bounds__(32 * (TY + 4 - 2 * FOLD), 1) hydro_step_kernel
   const int lane = threadIdx.x, row = threadIdx.y + FOLD;
   const int xg = g.gw + blockIdx.x * HTX + lane - 2; // ghosted coordinates of this thread's column
   const int yg = g.gw + blockIdx.y * TY + row - 2;
-  const int so = row * 32 + lane; // offset inside one smem variable plane
+  const int so = row * 32 + lane; // offset inside one variable plane of the primitive ring
+  const int so2 = so - 32;        // ... of the face-state / flux / update planes (rows 1 .. TY+2 only)
 
   const bool inb = (xg < g.isize) && (yg < g.jsize);
   // cells whose slopes/trace are needed: the tile plus a 1-cell ring (inside the ghosted box)
@@ -218,8 +222,8 @@ __global__ void __launch_bounds__(32 * (TY + 4 - 2 * FOLD), 1) hydro_step_kernel
           mxv = dmax(g.smallr, mxv);
           myv = dmax(g.smallr, myv);
         }
-        sm.mx[v * PLANE + so] = mxv;
-        sm.my[v * PLANE + so] = myv;
+        sm.mx[v * PLANE2 + so2] = mxv;
+        sm.my[v * PLANE2 + so2] = myv;
         if constexpr (DIM == 3) {
           const double bz0 = fma(s[v], dth[2], qc[v]);
           double bzl = bz0, bzh = bz0;
@@ -235,7 +239,7 @@ __global__ void __launch_bounds__(32 * (TY + 4 - 2 * FOLD), 1) hydro_step_kernel
             lo[2][v] = dmax(g.smallr, lo[2][v]);
             mzv = dmax(g.smallr, mzv);
           }
-          sm.mz[zb][v * PLANE + so] = mzv;
+          sm.mz[zb][v * PLANE2 + so2] = mzv;
         }
       }
     } else {
@@ -258,12 +262,12 @@ __global__ void __launch_bounds__(32 * (TY + 4 - 2 * FOLD), 1) hydro_step_kernel
       double ql[3][5], qr[3][5], f[3][5];
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
-        ql[0][v] = sm.mx[v * PLANE + so - 1];
-        ql[1][v] = sm.my[v * PLANE + so - 32];
+        ql[0][v] = sm.mx[v * PLANE2 + so2 - 1];
+        ql[1][v] = sm.my[v * PLANE2 + so2 - 32];
         qr[0][v] = lo[0][v];
         qr[1][v] = lo[1][v];
         if constexpr (DIM == 3) {
-          ql[2][v] = sm.mz[zb ^ 1][v * PLANE + so];
+          ql[2][v] = sm.mz[zb ^ 1][v * PLANE2 + so2];
           qr[2][v] = lo[2][v];
         }
       }
@@ -283,14 +287,14 @@ __global__ void __launch_bounds__(32 * (TY + 4 - 2 * FOLD), 1) hydro_step_kernel
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
           fl[0][v] = f[0][v] * dtd[0];
-          sm.fx[v * PLANE + so] = fl[0][v];
+          sm.fx[v * PLANE2 + so2] = fl[0][v];
         }
       }
       if (do_fy) {
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
           fl[1][v] = f[1][v] * dtd[1];
-          sm.fy[v * PLANE + so] = fl[1][v];
+          sm.fy[v * PLANE2 + so2] = fl[1][v];
         }
       }
       if constexpr (DIM == 3) {
@@ -315,7 +319,7 @@ __global__ void __launch_bounds__(32 * (TY + 4 - 2 * FOLD), 1) hydro_step_kernel
           double un[NV];
 #pragma unroll
           for (int v = 0; v < NV; ++v)
-            un[v] = sm.part[0][v * PLANE + so] - fl[2][v];
+            un[v] = sm.part[0][v * PLANE2 + so2] - fl[2][v];
           const long long o = col + g.sk * (p - 1);
           double gv[3] = { 0.0, 0.0, 0.0 };
           if constexpr (GRAV) {
@@ -343,11 +347,11 @@ __global__ void __launch_bounds__(32 * (TY + 4 - 2 * FOLD), 1) hydro_step_kernel
           for (int v = 0; v < NV; ++v) {
             double u = __ldg(Uin + o + g.sv * v);
             u += fl[0][v];
-            u -= sm.fx[v * PLANE + so + 1];
+            u -= sm.fx[v * PLANE2 + so2 + 1];
             u += fl[1][v];
-            u -= sm.fy[v * PLANE + so + 32];
+            u -= sm.fy[v * PLANE2 + so2 + 32];
             u += fl[2][v];
-            sm.part[0][v * PLANE + so] = u;
+            sm.part[0][v * PLANE2 + so2] = u;
           }
         }
       } else {
@@ -356,9 +360,9 @@ __global__ void __launch_bounds__(32 * (TY + 4 - 2 * FOLD), 1) hydro_step_kernel
         for (int v = 0; v < NV; ++v) {
           double u = __ldg(Uin + col + g.sv * v);
           u += fl[0][v];
-          u -= sm.fx[v * PLANE + so + 1];
+          u -= sm.fx[v * PLANE2 + so2 + 1];
           u += fl[1][v];
-          u -= sm.fy[v * PLANE + so + 32];
+          u -= sm.fy[v * PLANE2 + so2 + 32];
           un[v] = u;
         }
         double gv[3] = { 0.0, 0.0, 0.0 };

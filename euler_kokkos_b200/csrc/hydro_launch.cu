@@ -19,6 +19,9 @@ constexpr int TY = EK_HYDRO_TY;
 #define EK_HYDRO_TYF 14
 #endif
 constexpr int TYF = EK_HYDRO_TYF;
+// (Measured in round 2 and removed: folded rows on a 28 x 6 tile, 8 warps, TWO resident CTAs per SM whose barriers are
+//  independent -- 11.96 ms against 10.88 on blast 512^3, 36.1 against 35.0 on Rayleigh-Taylor: the de-phasing of the two
+//  CTAs does not pay for 13 % more traces and 7 % more Riemann problems per cell of the smaller tile.)
 
 // 3-D tile layout: 1 = folded halo rows, 28 x 14 tile, 16 warps; 0 = one warp per tile row incl. halo rows, 28 x 11,
 // 15 warps.  Measured at 512^3 (profiles/r01_hydro_fold_ncu.txt): the folded layout executes 3.4 % fewer
@@ -68,12 +71,13 @@ static ZPlan z_plan(const Ctx& c, long long xy_ctas, bool want_split)
 {
   ZPlan z;
   const int nz = c.g.nz, gw = c.g.gw;
-  z.zchunk = pick_zchunk(nz, xy_ctas, c.sm_count);
+  const int slots = c.sm_count; // one resident CTA per SM
+  z.zchunk = pick_zchunk(nz, xy_ctas, slots);
   z.nchunk = (nz + z.zchunk - 1) / z.zchunk;
   z.splittable = false;
   if (!want_split)
     return z;
-  const int zc = (z.nchunk >= 3) ? z.zchunk : pick_zchunk(nz, xy_ctas, c.sm_count, 3, gw);
+  const int zc = (z.nchunk >= 3) ? z.zchunk : pick_zchunk(nz, xy_ctas, slots, 3, gw);
   const int nc = (nz + zc - 1) / zc;
   const int last = nz - (nc - 1) * zc;
   if (nc >= 3 && zc >= gw && last >= gw) {
