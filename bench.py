@@ -124,12 +124,14 @@ def config_dict(args, world):
             "decomposition": "1 z-slab per GPU, NCCL halos" if world > 1 else "single domain"}
 
 
-def kernel_sources_hash():
-    """identifies the kernels a recorded ncu capture belongs to (profiles/traffic.json)"""
+def kernel_sources_hash(fam="mhd"):
+    """identifies the kernels a recorded ncu capture belongs to (profiles/traffic.json): the sources of that solver
+    family's kernels (mhd_*.cu* or hydro_*.cu*) + the shared arithmetic header"""
     h = hashlib.sha1()
     d = os.path.join(ROOT, "euler_kokkos_b200", "csrc")
+    prefix = "mhd_" if fam.startswith("mhd") else "hydro_"
     for fn in sorted(os.listdir(d)):
-        if fn.endswith((".cu", ".cuh")):
+        if fn.endswith((".cu", ".cuh")) and (fn.startswith(prefix) or fn == "ek_common.cuh"):
             with open(os.path.join(d, fn), "rb") as f:
                 h.update(fn.encode() + b"\0" + f.read())
     return h.hexdigest()[:12]
@@ -143,7 +145,7 @@ def recorded_capture(fam, nx, ny, nz):
             d = json.load(f)
         key = f"{fam.replace('_grav', '')}@{nx}"
         rec = d.get(key)
-        if rec and nx == ny == nz and not fam.endswith("_grav") and rec.get("kernels_sha1") == kernel_sources_hash():
+        if rec and nx == ny == nz and not fam.endswith("_grav") and rec.get("kernels_sha1") == kernel_sources_hash(fam):
             return rec
     except Exception:
         pass

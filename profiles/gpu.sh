@@ -29,7 +29,7 @@ for STEP in "$@"; do
       python profiles/summarize.py launches $O/${TAG}_launches.csv | tee $O/${TAG}_launches.txt ;;
     metrics)
       M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum,sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active,smsp__inst_executed.sum,smsp__thread_inst_executed.sum,sm__inst_executed_pipe_fp64.sum,sm__warps_active.avg.pct_of_peak_sustained_active
-      timeout 900 ncu --metrics $M --clock-control none -k regex:"$A" -s 12 -c 12 --csv --log-file $O/${TAG}_metrics.csv \
+      timeout 900 ncu --metrics $M --clock-control none -k regex:"$A" -s ${MSKIP:-12} -c ${MCOUNT:-12} --csv --log-file $O/${TAG}_metrics.csv \
         python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-secondary $(args "$B") > $O/${TAG}_metrics.log 2>&1; echo "[$STEP] rc=$?"
       python profiles/summarize.py metrics $O/${TAG}_metrics.csv | tee $O/${TAG}_metrics.txt ;;
     ncu)

@@ -54,9 +54,9 @@ def main():
         d = {}
     d["_comment"] = ("per-STEP DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum), FP64-pipe thread instructions per cell and "
                      "time-weighted FP64-pipe utilisation of the step kernels, from the ncu metrics pass named in 'source'; "
-                     "bench.py quotes an entry only while 'kernels_sha1' equals the hash of euler_kokkos_b200/csrc/*.cu*")
+                     "bench.py quotes an entry only while 'kernels_sha1' equals the hash of that family's kernel sources (euler_kokkos_b200/csrc/mhd_* or hydro_*, + ek_common.cuh)")
     d[key] = {"traffic_bytes": tot_bytes, "fp64_thread_inst_per_cell": tot_fp64 / cells, "fp64_pipe_active_frac": pipe_ms / tot_ms,
-              "kernels": kernels, "kernels_sha1": bench.kernel_sources_hash(), "source": source}
+              "kernels": kernels, "kernels_sha1": bench.kernel_sources_hash(key.split("@")[0]), "source": source}
     with open(out_path, "w") as f:
         json.dump(d, f, indent=1)
     print(json.dumps(d[key], indent=1))
