@@ -187,3 +187,66 @@ def test_mhd3d_2x2x2_periodic_on_eight_gpus(tmp_path):
 
 def test_mhd2d_2x2_on_four_gpus(tmp_path):
     _run_cart("test_mhd_orszag_tang_2D.ini", {"mesh.nx": 32, "mesh.ny": 24, "mesh.nz": 1}, (2, 2, 1), 8, tmp_path, 1e-13)
+
+
+# ---- the C++ driver itself on several ranks (one process per GPU, NCCL id through the rendezvous file) -------------
+@pytest.mark.parametrize("ini_name,ov,dims", [
+    ("test_mhd_orszag_tang_3D.ini", {"mesh.nx": 24, "mesh.ny": 20, "mesh.nz": 12}, (1, 1, 2)),
+    ("test_implode_3D.ini", {"mesh.nx": 20, "mesh.ny": 24, "mesh.nz": 16}, (2, 1, 1)),
+])
+def test_euler_b200_executable_on_two_ranks_writes_the_single_domain_state(tmp_path, ini_name, ov, dims):
+    """`torchrun --no-python --nproc-per-node 2 bin/euler_b200 file.ini` with an [mpi] section: the ranks find each
+    other through the per-launch rendezvous file (comm_rendezvous.cpp), exchange halos over NCCL, and write a .pvti
+    collection whose assembled last dump equals the single-process run of the same global grid (the reference needs an
+    MPI build for this, main.cpp:54-111)."""
+    import glob
+    import subprocess
+    import sys
+
+    import torch
+
+    world = dims[0] * dims[1] * dims[2]
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    from euler_kokkos_b200 import hostapi
+    from euler_kokkos_b200.vti import read_pvti, read_vti
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    binary = os.path.join(root, "euler_kokkos_b200", "bin", "euler_b200")
+    common = {"run.nstepmax": 6, "run.tend": 1e6, "run.noutput": -1, "run.nlog": 2, "output.outputprefix": "g",
+              "output.hdf5_enabled": "no", "output.vtk_enabled": "yes"}
+    # decomposed
+    dmulti = tmp_path / "multi"
+    dmulti.mkdir()
+    o = dict(ov)
+    o.update(common)
+    o.update({"mpi.mx": dims[0], "mpi.my": dims[1], "mpi.mz": dims[2], "output.outputdir": str(dmulti)})
+    ini_m = str(dmulti / "case.ini")
+    hostapi.write_ini(hostapi.settings(ini_name), o, ini_m)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--no-python", "--nnodes=1", f"--nproc-per-node={world}",
+                        "--master-addr", "127.0.0.1", "--master-port", "29577", binary, ini_m],
+                       cwd=str(dmulti), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    assert not glob.glob("/tmp/ek_b200_rdv_29577_*"), "rank 0 removes the rendezvous file once the communicator is up"
+    # single domain, same global grid
+    dsingle = tmp_path / "single"
+    dsingle.mkdir()
+    o1 = dict(ov)
+    o1.update(common)
+    o1.update({"mesh.nx": ov["mesh.nx"] * dims[0], "mesh.ny": ov["mesh.ny"] * dims[1], "mesh.nz": ov["mesh.nz"] * dims[2],
+               "output.outputdir": str(dsingle)})
+    ini_s = str(dsingle / "case.ini")
+    hostapi.write_ini(hostapi.settings(ini_name), o1, ini_s)
+    r1 = subprocess.run([binary, ini_s], cwd=str(dsingle), capture_output=True, text=True, timeout=600)
+    assert r1.returncode == 0, r1.stdout[-1500:] + r1.stderr[-1500:]
+    # same log lines from rank 0 as from the single process
+    from tests.util import log_lines
+    assert log_lines(r.stdout) == log_lines(r1.stdout)
+    pv = sorted(glob.glob(str(dmulti / "g_time*.pvti")))
+    sv = sorted(glob.glob(str(dsingle / "g_*.vti")))
+    assert len(pv) == len(sv) and len(pv) >= 7
+    names_m, got = read_pvti(pv[-1])
+    names_s, ref = read_vti(sv[-1])
+    assert names_m == names_s
+    den = np.abs(ref).max(axis=(1, 2, 3), keepdims=True) + 1e-300
+    assert (np.abs(got - ref) / den).max() <= 1e-13
