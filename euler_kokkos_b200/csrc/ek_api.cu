@@ -42,22 +42,23 @@ __global__ void pre_step_kernel(TimeState* ts, double cfl, int use_host_dt, doub
 }
 
 // ++iteration; t += dt; finished? (SolverBase::next_iteration / finished, SolverBase.cpp:171-195)
-__global__ void post_step_kernel(TimeState* ts, int max_steps)
+__global__ void post_step_kernel(TimeState* ts)
 {
   if (ts->finished)
     return;
   ts->t += ts->dt;
   ts->steps_done += 1;
-  if (ts->t >= ts->t_end - 1e-14 || ts->steps_done >= max_steps)
+  if (ts->t >= ts->t_end - 1e-14 || ts->steps_done >= ts->max_steps)
     ts->finished = 1;
 }
 
-__global__ void reset_time_kernel(TimeState* ts, double t, double t_end)
+__global__ void reset_time_kernel(TimeState* ts, double t, double t_end, int max_steps)
 {
   ts->t = t;
   ts->t_end = t_end;
   ts->steps_done = 0;
   ts->finished = 0;
+  ts->max_steps = max_steps;
 }
 
 // ---- diagnostics ---------------------------------------------------------------------------------
@@ -280,7 +281,7 @@ static int prime_invdt(Ctx& c)
 }
 
 // one godunov_unsplit on the stream; dt comes from the device (use_host_dt = 0) or from the host
-static int enqueue_step(Ctx& c, int use_host_dt, double host_dt, int max_steps)
+static int enqueue_step(Ctx& c, int use_host_dt, double host_dt)
 {
   double* Uin = c.U[c.cur];
   double* Uout = c.U[1 - c.cur];
@@ -356,7 +357,7 @@ static int enqueue_step(Ctx& c, int use_host_dt, double host_dt, int max_steps)
     c.dt_primed = true;
   }
   c.ghosts_valid_for = nullptr; // the new level's ghosts are not filled yet
-  post_step_kernel<<<1, 1, 0, c.stream>>>(c.ts, max_steps);
+  post_step_kernel<<<1, 1, 0, c.stream>>>(c.ts);
   c.launches++;
   EK_CUDA(&c, cudaGetLastError());
   return EK_OK;
@@ -460,6 +461,10 @@ int ek_destroy(ek_ctx* ctx)
   ek_comm_detach(ctx);
   for (cudaEvent_t e : c->kev) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamSynchronize(c->own_stream);
+  for (cudaGraphExec_t& ge : c->step_graph) {
+    if (ge) cudaGraphExecDestroy(ge);
+    ge = nullptr;
+  }
   if (c->aux_stream) cudaStreamSynchronize(c->aux_stream);
   if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
   cudaFree(c->U[0]); cudaFree(c->U[1]); cudaFree(c->grav); cudaFree(c->work); cudaFree(c->ts); cudaFree(c->scratch);
@@ -597,9 +602,9 @@ int ek_step(ek_ctx* ctx, double dt)
   if (!ctx) return EK_ERR_INVALID;
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
   EK_CUDA(c, cudaSetDevice(c->device));
-  reset_time_kernel<<<1, 1, 0, c->stream>>>(c->ts, 0.0, 1e300);
+  reset_time_kernel<<<1, 1, 0, c->stream>>>(c->ts, 0.0, 1e300, 1 << 30);
   c->launches++;
-  int rc = enqueue_step(*c, 1, dt, 1 << 30);
+  int rc = enqueue_step(*c, 1, dt);
   if (rc != EK_OK)
     return rc;
   c->cur = 1 - c->cur;
@@ -608,18 +613,95 @@ int ek_step(ek_ctx* ctx, double dt)
   return EK_OK;
 }
 
+// Two consecutive steps of the device-resident loop captured as a CUDA graph (the level ping-pong makes a pair periodic).
+// For launch-bound grids (configs[0]: 1024 x 512 cells, 49 us of kernels in a 74 us step) the five launches of a step
+// cost as much as a third of the work; a replay submits ten of them at once.  Single GPU only (no NCCL calls, one
+// stream); not while per-kernel event timing is on.  EK_GRAPH=1 / 0 forces / forbids it; default: grids below 4 M cells.
+static bool graph_wanted(const Ctx& c, int nsteps)
+{
+  if (c.nranks != 1 || c.nccl_comm || c.ktiming || nsteps < 3)
+    return false;
+  const char* e = getenv("EK_GRAPH");
+  if (e)
+    return atoi(e) != 0;
+  return (long long)c.g.nx * c.g.ny * c.g.nz < (4LL << 20);
+}
+
+static int capture_step_pair(Ctx& c)
+{
+  const int par = c.cur;
+  cudaGraph_t graph = nullptr;
+  const int64_t l0 = c.launches;
+  EK_CUDA(&c, cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeThreadLocal));
+  int rc = EK_OK;
+  for (int s = 0; s < 2 && rc == EK_OK; ++s) {
+    rc = enqueue_step(c, 0, 0.0);
+    c.cur = 1 - c.cur;
+  }
+  cudaError_t e = cudaStreamEndCapture(c.stream, &graph);
+  c.launches = l0; // nothing ran: the replays are counted
+  if (rc != EK_OK) {
+    if (graph) cudaGraphDestroy(graph);
+    return rc;
+  }
+  if (e != cudaSuccess || !graph) {
+    c.err = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e);
+    return EK_ERR_CUDA;
+  }
+  // kernels of one replay (memset nodes etc. are not launches of ours)
+  size_t nodes = 0, kernels = 0;
+  cudaGraphGetNodes(graph, nullptr, &nodes);
+  std::vector<cudaGraphNode_t> nv(nodes);
+  if (nodes && cudaGraphGetNodes(graph, nv.data(), &nodes) == cudaSuccess) {
+    for (cudaGraphNode_t nd : nv) {
+      cudaGraphNodeType ty;
+      if (cudaGraphNodeGetType(nd, &ty) == cudaSuccess && ty == cudaGraphNodeTypeKernel)
+        ++kernels;
+    }
+  }
+  e = cudaGraphInstantiate(&c.step_graph[par], graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) {
+    c.step_graph[par] = nullptr;
+    c.err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e);
+    return EK_ERR_CUDA;
+  }
+  c.graph_kernels[par] = (int64_t)kernels;
+  return EK_OK;
+}
+
 int ek_run(ek_ctx* ctx, int nsteps, double t, double t_end, double* t_out, double* dt_last_out, int* steps_done_out)
 {
   if (!ctx || nsteps < 0) return EK_ERR_INVALID;
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
   EK_CUDA(c, cudaSetDevice(c->device));
-  reset_time_kernel<<<1, 1, 0, c->stream>>>(c->ts, t, t_end);
+  reset_time_kernel<<<1, 1, 0, c->stream>>>(c->ts, t, t_end, nsteps);
   c->launches++;
   // SolverBase::finished() is evaluated before the first iteration too
   if (t >= t_end - 1e-14)
     nsteps = 0;
-  for (int s = 0; s < nsteps; ++s) {
-    int rc = enqueue_step(*c, 0, 0.0, nsteps);
+  int s = 0;
+  if (graph_wanted(*c, nsteps)) {
+    // the first step runs as plain launches: it primes the CFL reduction and leaves the flags in their steady state
+    int rc = enqueue_step(*c, 0, 0.0);
+    if (rc != EK_OK)
+      return rc;
+    c->cur = 1 - c->cur;
+    s = 1;
+    const int par = c->cur;
+    if (!c->step_graph[par] && capture_step_pair(*c) != EK_OK) {
+      c->step_graph[par] = nullptr; // not capturable here: the plain loop below takes over
+      cudaGetLastError();
+    }
+    if (c->step_graph[par]) {
+      for (; nsteps - s >= 2; s += 2) {
+        EK_CUDA(c, cudaGraphLaunch(c->step_graph[par], c->stream));
+        c->launches += c->graph_kernels[par];
+      }
+    }
+  }
+  for (; s < nsteps; ++s) {
+    int rc = enqueue_step(*c, 0, 0.0);
     if (rc != EK_OK)
       return rc;
     c->cur = 1 - c->cur; // provisional; corrected below if the loop finished early on the device

@@ -24,6 +24,7 @@ struct TimeState {
   unsigned long long invdt_bits; // running max of invDt (bit pattern of a non-negative double)
   int steps_done;
   int finished;
+  int max_steps; // iterations after which the loop is finished (device resident so that a captured graph does not bake it in)
 };
 
 // Geometry + physics constants handed to every kernel by value (constant bank).

@@ -41,6 +41,10 @@ struct Ctx {
   // level whose CFL maximum (all interior cells but the last layers) the update kernel has left in ts->invdt_bits
   const double* mhd_dt_partial_for = nullptr;
   int sm_count = 148;
+  // device-resident time loop as a CUDA graph (single GPU, launch-bound grids): two consecutive steps captured once per
+  // starting level, replayed by ek_run; the kernels launched by one replay are counted in graph_kernels
+  cudaGraphExec_t step_graph[2] = { nullptr, nullptr };
+  int64_t graph_kernels[2] = { 0, 0 };
   const void* smem_attr_for = nullptr; // hydro step kernel whose dynamic shared-memory limit has been raised on this device
   bool mhd_pet_attr = false; // dynamic shared-memory limit of mhd_pet_kernel raised on this device
   // TMA descriptors of the two time levels as 4-D tensors (x, y, z, variable) for the TMA-fed P+E+T kernel
