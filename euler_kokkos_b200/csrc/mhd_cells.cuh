@@ -33,13 +33,16 @@ EK_HD size_t tile_off(unsigned c)
 }
 constexpr int TL = 32; // stride between variables inside a tile
 
-// work-array layout, in units of one padded cell-array (mhd_padded_cells doubles)
+// work-array layout, in units of one padded cell-array (mhd_padded_cells doubles).  The product's 3-D kernels keep the
+// primitives and the edge field in shared memory (mhd_pet*.cuh), so the library allocates W3_DEVICE arrays only; the
+// staged per-cell functions (CPU emulation of the tests) also use Q and E, placed after them.
 enum : int {
-  WQ = 0,         // primitives, 8
-  WE = 8,         // edge electric field Ex,Ey,Ez at the lower edges, 3
-  WS = 11,        // compact half-step state, 38
-  WF = 49,        // face fluxes Fx,Fy,Fz x (mass, energy, mom_x, mom_y, mom_z), 15
-  WEMF = 64,      // EMFs at the lower edges: Ex, Ey, Ez, 3
+  WS = 0,         // compact half-step state, 38
+  WF = 38,        // face fluxes Fx,Fy,Fz x (mass, energy, mom_x, mom_y, mom_z), 15
+  WEMF = 53,      // EMFs at the lower edges: Ex, Ey, Ez, 3
+  W3_DEVICE = 56, // what libek_b200 allocates for MHD_Muscl_3D (512^3: 62.3 GB)
+  WQ = 56,        // primitives, 8                                   (emulation only)
+  WE = 64,        // edge electric field Ex,Ey,Ez at the lower edges, 3 (emulation only)
   W_TOTAL = 67
 };
 // compact state S
