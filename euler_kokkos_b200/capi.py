@@ -67,6 +67,10 @@ _protos = {
     "ek_state_len": (C.c_int64, [_vp]),
     "ek_upload_state": (C.c_int, [_vp, _vp]),
     "ek_download_state": (C.c_int, [_vp, _vp]),
+    "ek_download_state_async": (C.c_int, [_vp, _vp]),
+    "ek_download_wait": (C.c_int, [_vp]),
+    "ek_alloc_host": (C.c_int, [C.c_size_t, C.POINTER(_vp)]),
+    "ek_free_host": (C.c_int, [_vp]),
     "ek_device_state": (C.c_int, [_vp, C.POINTER(_vp)]),
     "ek_set_gravity": (C.c_int, [_vp, _vp]),
     "ek_fill_boundaries": (C.c_int, [_vp]),
@@ -139,6 +143,13 @@ class Context:
 
     def upload(self, U):
         self._ck(lib.ek_upload_state(self._h, _ptr(U)))
+
+    def download_async(self, out):
+        """snapshot the current level and start its copy to `out` (pinned memory overlaps with later steps)"""
+        self._ck(lib.ek_download_state_async(self._h, _ptr(out)))
+
+    def download_wait(self):
+        self._ck(lib.ek_download_wait(self._h))
 
     def download(self, out=None):
         if out is None:

@@ -461,6 +461,12 @@ int ek_destroy(ek_ctx* ctx)
   ek_comm_detach(ctx);
   for (cudaEvent_t e : c->kev) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamSynchronize(c->own_stream);
+  if (c->io_stream) {
+    cudaStreamSynchronize(c->io_stream);
+    cudaStreamDestroy(c->io_stream);
+  }
+  if (c->ev_snap) cudaEventDestroy(c->ev_snap);
+  cudaFree(c->snap);
   for (cudaGraphExec_t& ge : c->step_graph) {
     if (ge) cudaGraphExecDestroy(ge);
     ge = nullptr;
@@ -540,6 +546,62 @@ int ek_download_state(ek_ctx* ctx, double* U_host)
   EK_CUDA(c, cudaSetDevice(c->device));
   EK_CUDA(c, cudaMemcpyAsync(U_host, c->U[c->cur], (size_t)c->state_len * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   EK_CUDA(c, cudaStreamSynchronize(c->stream));
+  return EK_OK;
+}
+
+int ek_alloc_host(size_t bytes, void** out)
+{
+  if (!out) return EK_ERR_INVALID;
+  *out = nullptr;
+  if (cudaMallocHost(out, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    g_create_err = "cudaMallocHost failed";
+    return EK_ERR_CUDA;
+  }
+  return EK_OK;
+}
+
+int ek_free_host(void* p)
+{
+  if (p) cudaFreeHost(p);
+  return EK_OK;
+}
+
+int ek_download_wait(ek_ctx* ctx)
+{
+  if (!ctx) return EK_ERR_INVALID;
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  if (!c->io_pending)
+    return EK_OK;
+  EK_CUDA(c, cudaSetDevice(c->device));
+  EK_CUDA(c, cudaStreamSynchronize(c->io_stream));
+  c->io_pending = false;
+  return EK_OK;
+}
+
+int ek_download_state_async(ek_ctx* ctx, double* U_host)
+{
+  if (!ctx || !U_host) return EK_ERR_INVALID;
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  EK_CUDA(c, cudaSetDevice(c->device));
+  int rc = ek_download_wait(ctx); // one in flight: the snapshot buffer is about to be overwritten
+  if (rc != EK_OK)
+    return rc;
+  const size_t bytes = (size_t)c->state_len * sizeof(double);
+  if (!c->snap) {
+    if (cudaMalloc(&c->snap, bytes) != cudaSuccess) {
+      cudaGetLastError();
+      c->snap = nullptr;
+      return ek_download_state(ctx, U_host); // no room for a snapshot: the synchronous copy
+    }
+    EK_CUDA(c, cudaStreamCreateWithFlags(&c->io_stream, cudaStreamNonBlocking));
+    EK_CUDA(c, cudaEventCreateWithFlags(&c->ev_snap, cudaEventDisableTiming));
+  }
+  EK_CUDA(c, cudaMemcpyAsync(c->snap, c->U[c->cur], bytes, cudaMemcpyDeviceToDevice, c->stream));
+  EK_CUDA(c, cudaEventRecord(c->ev_snap, c->stream));
+  EK_CUDA(c, cudaStreamWaitEvent(c->io_stream, c->ev_snap, 0));
+  EK_CUDA(c, cudaMemcpyAsync(U_host, c->snap, bytes, cudaMemcpyDeviceToHost, c->io_stream));
+  c->io_pending = true;
   return EK_OK;
 }
 

@@ -27,6 +27,10 @@ struct Ctx {
   const double* halo_ready_for = nullptr;
   const double* ghosts_valid_for = nullptr; // level whose ghost cells are filled and exchanged (nothing has written it since)
   double* U[2] = { nullptr, nullptr }; // ping-pong levels
+  double* snap = nullptr;              // device snapshot of a level for ek_download_state_async (allocated on first use)
+  cudaStream_t io_stream = nullptr;    // its device -> host copy runs here, beside the stepping
+  cudaEvent_t ev_snap = nullptr;
+  bool io_pending = false;
   int cur = 0;                         // index of the current level
   double* grav = nullptr;
   double* work = nullptr;   // solver scratch (MHD: staged arrays)

@@ -24,8 +24,17 @@ SolverMusclB200::SolverMusclB200(HydroParams& params_, ConfigMap& configMap_)
 
 SolverMusclB200::~SolverMusclB200()
 {
+  finish_pending_output();
+  if (m_io_buf)
+    ek_free_host(m_io_buf);
   if (m_ctx)
     ek_destroy(m_ctx);
+}
+
+void SolverMusclB200::finish_pending_output()
+{
+  if (m_io_thread.joinable())
+    m_io_thread.join();
 }
 
 void SolverMusclB200::check(int rc, const char* what)
@@ -55,6 +64,7 @@ void SolverMusclB200::construct()
   }
   const size_t n = (size_t)ek_state_len(m_ctx);
   m_Uhost.assign(n, 0.0);
+  m_async_io = configMap.getBool("output", "async_io", true);
   std::vector<double> grav;
   if (params.gravity.enabled)
     grav.assign((size_t)isize * jsize * ksize * params.dimType, 0.0);
@@ -162,8 +172,27 @@ void SolverMusclB200::save_solution_impl()
     std::exit(EXIT_FAILURE);
   }
   timers[TIMER_IO]->start();
-  host_state();
-  save_vti(m_Uhost.data(), params, configMap, params.nbvar, m_variables_names, m_times_saved);
+  finish_pending_output(); // at most one dump in flight: its buffer and the device snapshot are reused
+  if (m_async_io && !m_io_buf) {
+    void* p = nullptr;
+    if (ek_alloc_host(m_Uhost.size() * sizeof(double), &p) == EK_OK)
+      m_io_buf = static_cast<double*>(p);
+    else
+      m_async_io = false; // no page-locked memory: synchronous dumps
+  }
+  if (m_async_io) {
+    // SolverHydroMuscl::save_solution_impl copies, then writes; here the copy is a device snapshot taken NOW (ordered
+    // on the stream, so it is the state of this iteration) and the write happens beside the next iterations
+    check(ek_download_state_async(m_ctx, m_io_buf), "ek_download_state_async");
+    const int step = m_times_saved;
+    m_io_thread = std::thread([this, step] {
+      if (ek_download_wait(m_ctx) == EK_OK)
+        save_vti(m_io_buf, params, configMap, params.nbvar, m_variables_names, step);
+    });
+  } else {
+    host_state();
+    save_vti(m_Uhost.data(), params, configMap, params.nbvar, m_variables_names, m_times_saved);
+  }
   timers[TIMER_IO]->stop();
 }
 

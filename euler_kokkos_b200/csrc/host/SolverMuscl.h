@@ -6,6 +6,7 @@
 // ek_b200.h and one step is one fused launch sequence; there are no Q / flux / slope / trace arrays.
 #pragma once
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../../include/ek_b200.h"
@@ -29,12 +30,19 @@ public:
   //! current state, ghosts included, SoA [var][k][j][i] (downloads from the device)
   const std::vector<double>& host_state();
   ek_ctx* context() { return m_ctx; }
+  //! block until the dump started by the last save_solution() is on disk (asynchronous output)
+  void finish_pending_output();
 
 protected:
   void construct(); // allocation + init + first boundaries + first dt, as the reference's ctors
   void check(int rc, const char* what);
   ek_ctx* m_ctx = nullptr;
   std::vector<double> m_Uhost;
+  // asynchronous output ([output] async_io, default yes): the dump is a device snapshot that travels to a page-locked
+  // buffer on its own stream and is written by a helper thread while the next iterations run
+  double* m_io_buf = nullptr;
+  std::thread m_io_thread;
+  bool m_async_io = false;
   int isize, jsize, ksize;
 };
 

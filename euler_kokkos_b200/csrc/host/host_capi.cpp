@@ -153,7 +153,13 @@ void ekh_solver_destroy(void* h) { delete static_cast<HostSolver*>(h); }
 int ekh_solver_finished(void* h) { return static_cast<HostSolver*>(h)->solver->finished(); }
 void ekh_solver_next_iteration(void* h) { static_cast<HostSolver*>(h)->solver->next_iteration(); }
 int ekh_solver_advance(void* h, int n) { return static_cast<HostSolver*>(h)->solver->advance(n); }
-void ekh_solver_save_solution(void* h) { static_cast<HostSolver*>(h)->solver->save_solution(); }
+void ekh_solver_save_solution(void* h)
+{
+  SolverBase* b = static_cast<HostSolver*>(h)->solver;
+  b->save_solution();
+  if (SolverMusclB200* m = dynamic_cast<SolverMusclB200*>(b))
+    m->finish_pending_output(); // a caller of this C function expects the file to exist when it returns
+}
 // out[0]=m_t, out[1]=m_dt, out[2]=m_iteration, out[3]=m_times_saved, out[4]=m_nCells, out[5]=state length (doubles)
 int ekh_solver_info(void* h, double* out)
 {

@@ -102,6 +102,15 @@ int ek_upload_state(ek_ctx* ctx, const double* U_host);
 /* Current time level -> host (ghosted SoA).  Replaces Kokkos::deep_copy(Uhost,Udata) in
  * save_solution_impl (src/muscl/SolverHydroMuscl.h:751-762). Synchronises. */
 int ek_download_state(ek_ctx* ctx, double* U_host);
+/* Asynchronous variant for output that overlaps the stepping: the current level is snapshot on the
+ * device (D2D, ordered on the handle's stream, a few ms), then copied to U_host -- pinned memory for a real overlap --
+ * on a separate stream while later steps run.  ek_download_wait blocks until that copy has landed (and is implied by the
+ * next ek_download_state_async and by ek_destroy).  One download in flight per handle. */
+int ek_download_state_async(ek_ctx* ctx, double* U_host);
+/* page-locked host memory for it (cudaMallocHost / cudaFreeHost: the host layer does not link the CUDA runtime itself) */
+int ek_alloc_host(size_t bytes, void** out);
+int ek_free_host(void* p);
+int ek_download_wait(ek_ctx* ctx);
 /* Device pointer to the current time level (for zero-copy callers holding device memory). */
 int ek_device_state(ek_ctx* ctx, double** dptr);
 /* Static gravity field g[3 or 2][k][j][i] (src/muscl/SolverHydroMuscl.h:268-272). */
