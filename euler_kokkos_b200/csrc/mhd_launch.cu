@@ -11,7 +11,7 @@ size_t mhd_work_bytes(const Grid& g)
   return (size_t)(g.ksize > 1 ? W3_DEVICE : W2_TOTAL) * (size_t)mhd_padded_cells(g.sv) * sizeof(double);
 }
 
-// 4-D tensor maps (x, y, z, variable) over both time levels, box = 36 x 19 x 1 x {8 | 1} doubles, no swizzle, zero fill
+// 4-D tensor maps (x, y, z, variable) over both time levels, box = 36 x 19 x 1 x 1 doubles, no swizzle, zero fill
 // outside the array.  The encoder is a driver entry point: looked up at run time, libcuda is not linked.
 bool mhd_make_tensor_maps(Ctx& c)
 {

@@ -18,8 +18,9 @@ for STEP in "$@"; do
   IFS=: read -r KIND A B <<< "$STEP"
   case $KIND in
     tests)
-      if [ -n "$A" ]; then SEL="-k $A"; [[ "$A" == tests/* ]] && SEL="$A"; else SEL=""; fi
-      timeout 1500 python -m pytest tests -m gpu -q $SEL > $O/${TAG}_pytest_gpu.log 2>&1; echo "[$STEP] rc=$?"; tail -4 $O/${TAG}_pytest_gpu.log ;;
+      WHAT=tests; SEL=""
+      if [ -n "$A" ]; then if [[ "$A" == tests/* ]]; then WHAT="$A"; else SEL="-k $A"; fi; fi
+      timeout 1500 python -m pytest $WHAT -m gpu -q $SEL > $O/${TAG}_pytest_gpu.log 2>&1; echo "[$STEP] rc=$?"; tail -4 $O/${TAG}_pytest_gpu.log ;;
     bench)
       SUF=$(echo "$A" | tr -c 'A-Za-z0-9\n' '_'); F=$O/${TAG}_bench${SUF:+_$SUF}.json
       timeout 900 python bench.py $(args "$A") > $F 2> ${F%.json}.err; echo "[$STEP] rc=$?"; cut -c1-420 $F; tail -2 ${F%.json}.err ;;
