@@ -485,7 +485,7 @@ EK_HD void mhd_stage_trace(const Grid& g, const double* __restrict__ U, const do
 // Sc: tile pointer of the cell (variable v at Sc[TL*v])
 // PRHO: pressure floor smallp*rho (2-D trace, MHDBaseFunctor2D.h:985-1100) instead of smallp (3-D, :908)
 // The value source is a "view" v with v(var) = variable var of the compact state S of one cell: a tile pointer
-// (TileRef, below) or the per-lane staging columns of the software-pipelined kernel (mhd_staged.cuh).
+// (TileRef, below); any other source of the 38 values of a cell can stand in.
 struct TileRef {
   const double* __restrict__ p;
   EK_HD double operator()(int var) const { return p[TL * var]; }

@@ -1,3 +1,4 @@
+// [Fallback of mhd_pet_tma.cuh for grids whose row length is odd (TMA needs 16-byte row strides), and EK_MHD_PET_TMA=0.]
 // Stages P + E + T of the CT-MHD step (primitives, edge electric field, Hancock predictor) fused in ONE kernel
 // that marches along z with the primitives and the edge field of the planes around the current one staged in
 // shared memory.  In the staged version these were three kernels talking through the Q (8 doubles/cell) and E (3)

@@ -323,6 +323,10 @@ EK_HD double mhd_emf2d_hlld(const Grid& g, const MhdCorner& LL, const MhdCorner&
   const double BstarRL = RL.b * fxRL, AstarRL = RL.a * fyRL;
   const double BstarRR = RR.b * fxRR, AstarRR = RR.a * fyRR;
 
+#ifndef EK_MHD_ALFVEN_SQ
+#define EK_MHD_ALFVEN_SQ 1
+#endif
+#if !EK_MHD_ALFVEN_SQ
   const double rstarLLx = LL.r * fxLL, rstarLLy = LL.r * fyLL, rstarLL = rstarLLx * fyLL;
   const double rstarLRx = LR.r * fxLR, rstarLRy = LR.r * fyLR, rstarLR = rstarLRx * fyLR;
   const double rstarRLx = RL.r * fxRL, rstarRLy = RL.r * fyRL, rstarRL = rstarRLx * fyRL;
@@ -337,6 +341,24 @@ EK_HD double mhd_emf2d_hlld(const Grid& g, const MhdCorner& LL, const MhdCorner&
                                     dmax(fabs(RL.b) * rsqrt_fast(rstarRLy), fabs(BstarRL) * isRL)), g.smallc);
   const double calfvenT = dmax(dmax(dmax(fabs(LR.b) * rsqrt_fast(rstarLRy), fabs(BstarLR) * isLR),
                                     dmax(fabs(RR.b) * rsqrt_fast(rstarRRy), fabs(BstarRR) * isRR)), g.smallc);
+
+#else
+  // Alfven speeds of the four outer states.  The reference takes, per state and direction, the larger of
+  //   |a| / sqrt(rho*)   with rho* = r fx            (compressed across the X wave only)   and
+  //   |a fy| / sqrt(rho**) with rho** = r fx fy      (compressed across both waves)
+  // (RiemannSolvers_MHD.h:480-560).  The second is the first times sqrt(fy) (fy > 0: it is a density ratio), so the pair
+  // is |a| sqrt(max(1, fy)) / sqrt(r fx); the maxima are taken over the SQUARES a^2 max(1, fy) / (r fx) and one square
+  // root per side follows: 8 reciprocals + 4 square roots instead of 12 reciprocal square roots.
+  const double sc2 = g.smallc * g.smallc;
+  const double tLLx = LL.a * LL.a * dmax(1.0, fyLL) * rcp_fast(LL.r * fxLL), tLLy = LL.b * LL.b * dmax(1.0, fxLL) * rcp_fast(LL.r * fyLL);
+  const double tLRx = LR.a * LR.a * dmax(1.0, fyLR) * rcp_fast(LR.r * fxLR), tLRy = LR.b * LR.b * dmax(1.0, fxLR) * rcp_fast(LR.r * fyLR);
+  const double tRLx = RL.a * RL.a * dmax(1.0, fyRL) * rcp_fast(RL.r * fxRL), tRLy = RL.b * RL.b * dmax(1.0, fxRL) * rcp_fast(RL.r * fyRL);
+  const double tRRx = RR.a * RR.a * dmax(1.0, fyRR) * rcp_fast(RR.r * fxRR), tRRy = RR.b * RR.b * dmax(1.0, fxRR) * rcp_fast(RR.r * fyRR);
+  const double calfvenL = sqrt_fast(dmax(dmax(tLRx, tLLx), sc2));
+  const double calfvenR = sqrt_fast(dmax(dmax(tRRx, tRLx), sc2));
+  const double calfvenB = sqrt_fast(dmax(dmax(tLLy, tRLy), sc2));
+  const double calfvenT = sqrt_fast(dmax(dmax(tLRy, tRRy), sc2));
+#endif
 
   const double SAL = dmin0(ustar - calfvenL), SAR = dmax0(ustar + calfvenR);
   const double SAB = dmin0(vstar - calfvenB), SAT = dmax0(vstar + calfvenT);
