@@ -102,9 +102,16 @@ EK_HD double limited_slope_ref(double st, double sk, double qm, double q, double
 
 // ---------------------------------------------------------------------------------------------
 // Division / square root.  EK_PRECISE_MATH=1 uses IEEE-rounded '/' and sqrt() everywhere (parity
-// bisecting build); the default uses MUFU seeds + FMA Newton steps without the IEEE special-case
-// slow paths (relative error <= ~1.5 ulp; operands here are always finite, normal and non-zero
+// bisecting build); the default uses MUFU seeds + ONE cubically convergent correction without the IEEE
+// special-case slow paths (relative error <= ~1.5 ulp; operands here are always finite, normal and non-zero
 // wherever these are used -- the callers floor densities/pressures first).
+// The 64-bit MUFU seeds carry ~23 bits (relative error e0 ~ 2^-23).  Two Newton steps (e -> e^2 -> e^4) were used in
+// round 1; one third-order step (e -> e^3 ~ 2^-69) is enough for a double and is one to three FP64 instructions
+// shorter: 1/x = y0 (1 + e + e^2 + O(e^3)) with e = 1 - x y0;  x^-1/2 = y0 (1 + e/2 + 3 e^2/8 + O(e^3)) with
+// e = 1 - x y0^2.  The MHD stage R executes ~84 reciprocals, ~51 square roots and ~6 reciprocal square roots per cell.
+#ifndef EK_CUBIC_SEEDS
+#define EK_CUBIC_SEEDS 1
+#endif
 // ---------------------------------------------------------------------------------------------
 #ifndef EK_PRECISE_MATH
 #define EK_PRECISE_MATH 0
@@ -117,11 +124,16 @@ EK_HD double rcp_fast(double x)
 #else
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#if EK_CUBIC_SEEDS
+  const double e = fma(-x, y, 1.0);
+  return fma(y, fma(e, e, e), y);
+#else
   double e = fma(-x, y, 1.0);
   y = fma(y, e, y);
   e = fma(-x, y, 1.0);
   y = fma(y, e, y);
   return y;
+#endif
 #endif
 }
 
@@ -130,10 +142,14 @@ EK_HD double div_fast(double a, double b)
 #if EK_PRECISE_MATH || !defined(__CUDA_ARCH__)
   return a / b;
 #else
+#if EK_CUBIC_SEEDS
+  return a * rcp_fast(b); // rcp_fast is within ~0.6 ulp after the cubic step: the product is within ~1.2 ulp
+#else
   double y = rcp_fast(b);
   double q = a * y;
   double r = fma(-b, q, a); // one residual correction: q is then within 1 ulp
   return fma(r, y, q);
+#endif
 #endif
 }
 
@@ -148,11 +164,15 @@ EK_HD double sqrt_fast(double x)
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
   double g = x * y;
   double h = 0.5 * y;
-  const double r = fma(-h, g, 0.5);
+  const double r = fma(-h, g, 0.5); // = e/2
+#if EK_CUBIC_SEEDS
+  g = fma(g, fma(1.5, r, 1.0) * r, g); // sqrt(x) = g0 (1 + r + 3 r^2 / 2 + O(r^3))
+#else
   g = fma(g, r, g);
   h = fma(h, r, h);
   const double d = fma(-g, g, x);
   g = fma(d, h, g);
+#endif
   return (x >= 2.2250738585072014e-308) ? g : 0.0;
 #endif
 }
@@ -168,10 +188,14 @@ EK_HD double sqrt_pos_fast(double x)
   double g = x * y;
   double h = 0.5 * y;
   const double r = fma(-h, g, 0.5);
+#if EK_CUBIC_SEEDS
+  return fma(g, fma(1.5, r, 1.0) * r, g);
+#else
   g = fma(g, r, g);
   h = fma(h, r, h);
   const double d = fma(-g, g, x);
   return fma(d, h, g);
+#endif
 #endif
 }
 
@@ -183,11 +207,16 @@ EK_HD double rsqrt_fast(double x)
 #else
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#if EK_CUBIC_SEEDS
+  const double e = fma(-x * y, y, 1.0);
+  return fma(y, fma(0.375, e, 0.5) * e, y);
+#else
   double e = fma(-x * y, y, 1.0);
   y = fma(y, 0.5 * e, y);
   e = fma(-x * y, y, 1.0);
   y = fma(y, 0.5 * e, y);
   return y;
+#endif
 #endif
 }
 
