@@ -74,9 +74,9 @@ EK_HD double mhd_cell_invdt(const Grid& g, const double* __restrict__ q)
   const double c2 = g.gamma0 * q[IP] * rd;
   const double d2 = 0.5 * (b2 * rd + c2);
   const double d22 = d2 * d2, c2r = c2 * rd;
-  const double cfx = sqrt_fast(d2 + sqrt_fast(dmax0(d22 - c2r * a * a)));
-  const double cfy = sqrt_fast(d2 + sqrt_fast(dmax0(d22 - c2r * b * b)));
-  const double cfz = sqrt_fast(d2 + sqrt_fast(dmax0(d22 - c2r * c * c)));
+  const double cfx = sqrt_pos_fast(d2 + sqrt_fast(dmax0(d22 - c2r * a * a))); // outer argument >= d2 > 0: no zero guard
+  const double cfy = sqrt_pos_fast(d2 + sqrt_fast(dmax0(d22 - c2r * b * b)));
+  const double cfz = sqrt_pos_fast(d2 + sqrt_fast(dmax0(d22 - c2r * c * c)));
   return (cfx + fabs(q[IU])) * g.invdx + (cfy + fabs(q[IV])) * g.invdy + (cfz + fabs(q[IW])) * g.invdz;
 }
 
@@ -116,7 +116,7 @@ EK_HD void mhd_hlld(const Grid& g, const MhdSide& L, const MhdSide& R, double a,
   const double ptotr = pr + emagr;
   const double vdotbr = ur * a + vr * br + wr * cr;
 
-  const double cfmax = sqrt_fast(dmax(mhd_fast_speed2(g.gamma0, rl, pl, a2, bt2l), mhd_fast_speed2(g.gamma0, rr, pr, a2, bt2r)));
+  const double cfmax = sqrt_pos_fast(dmax(mhd_fast_speed2(g.gamma0, rl, pl, a2, bt2l), mhd_fast_speed2(g.gamma0, rr, pr, a2, bt2r)));
   const double sl = dmin(ul, ur) - cfmax;
   const double sr = dmax(ul, ur) + cfmax;
 
@@ -234,7 +234,7 @@ EK_HD void mhd_hll(const Grid& g, const MhdSide& L, const MhdSide& R, double a, 
   mhd_side_flux(entho, L, a, ul, fl);
   mhd_side_flux(entho, R, a, ur, fr);
   const double a2 = a * a;
-  const double cmax = sqrt_fast(dmax(mhd_fast_speed2(g.gamma0, L.r, L.p, a2, L.bt1 * L.bt1 + L.bt2 * L.bt2),
+  const double cmax = sqrt_pos_fast(dmax(mhd_fast_speed2(g.gamma0, L.r, L.p, a2, L.bt1 * L.bt1 + L.bt2 * L.bt2),
                                      mhd_fast_speed2(g.gamma0, R.r, R.p, a2, R.bt1 * R.bt1 + R.bt2 * R.bt2)));
   const double sl = dmin0(dmin(L.un, R.un) - cmax);
   const double sr = dmax0(dmax(L.un, R.un) + cmax);
@@ -253,8 +253,8 @@ EK_HD void mhd_llf(const Grid& g, const MhdSide& L, const MhdSide& R, double a, 
   mhd_side_flux(entho, L, a, ul, fl);
   mhd_side_flux(entho, R, a, ur, fr);
   const double a2 = a * a;
-  const double cl = sqrt_fast(mhd_fast_speed2(g.gamma0, L.r, L.p, a2, L.bt1 * L.bt1 + L.bt2 * L.bt2)) + fabs(L.un);
-  const double cr = sqrt_fast(mhd_fast_speed2(g.gamma0, R.r, R.p, a2, R.bt1 * R.bt1 + R.bt2 * R.bt2)) + fabs(R.un);
+  const double cl = sqrt_pos_fast(mhd_fast_speed2(g.gamma0, L.r, L.p, a2, L.bt1 * L.bt1 + L.bt2 * L.bt2)) + fabs(L.un);
+  const double cr = sqrt_pos_fast(mhd_fast_speed2(g.gamma0, R.r, R.p, a2, R.bt1 * R.bt1 + R.bt2 * R.bt2)) + fabs(R.un);
   const double vel = dmax(cl, cr);
 #pragma unroll
   for (int v = 0; v < (BT2 ? 6 : 5); ++v)
@@ -293,8 +293,8 @@ EK_HD double mhd_emf2d_hlld(const Grid& g, const MhdCorner& LL, const MhdCorner&
     cfy[n] = d2 + sqrt_fast(dmax0(d22 - c2r * b2));
     ptot[n] = s.p + 0.5 * bb;
   }
-  const double cxm = sqrt_fast(dmax(dmax(cfx[0], cfx[1]), dmax(cfx[2], cfx[3])));
-  const double cym = sqrt_fast(dmax(dmax(cfy[0], cfy[1]), dmax(cfy[2], cfy[3])));
+  const double cxm = sqrt_pos_fast(dmax(dmax(cfx[0], cfx[1]), dmax(cfx[2], cfx[3]))); // fast speeds squared are > 0
+  const double cym = sqrt_pos_fast(dmax(dmax(cfy[0], cfy[1]), dmax(cfy[2], cfy[3])));
   const double SL = dmin(dmin(LL.u, LR.u), dmin(RL.u, RR.u)) - cxm;
   const double SR = dmax(dmax(LL.u, LR.u), dmax(RL.u, RR.u)) + cxm;
   const double SB = dmin(dmin(LL.v, LR.v), dmin(RL.v, RR.v)) - cym;
@@ -354,10 +354,10 @@ EK_HD double mhd_emf2d_hlld(const Grid& g, const MhdCorner& LL, const MhdCorner&
   const double tLRx = LR.a * LR.a * dmax(1.0, fyLR) * rcp_fast(LR.r * fxLR), tLRy = LR.b * LR.b * dmax(1.0, fxLR) * rcp_fast(LR.r * fyLR);
   const double tRLx = RL.a * RL.a * dmax(1.0, fyRL) * rcp_fast(RL.r * fxRL), tRLy = RL.b * RL.b * dmax(1.0, fxRL) * rcp_fast(RL.r * fyRL);
   const double tRRx = RR.a * RR.a * dmax(1.0, fyRR) * rcp_fast(RR.r * fxRR), tRRy = RR.b * RR.b * dmax(1.0, fxRR) * rcp_fast(RR.r * fyRR);
-  const double calfvenL = sqrt_fast(dmax(dmax(tLRx, tLLx), sc2));
-  const double calfvenR = sqrt_fast(dmax(dmax(tRRx, tRLx), sc2));
-  const double calfvenB = sqrt_fast(dmax(dmax(tLLy, tRLy), sc2));
-  const double calfvenT = sqrt_fast(dmax(dmax(tLRy, tRRy), sc2));
+  const double calfvenL = sqrt_pos_fast(dmax(dmax(tLRx, tLLx), sc2));
+  const double calfvenR = sqrt_pos_fast(dmax(dmax(tRRx, tRLx), sc2));
+  const double calfvenB = sqrt_pos_fast(dmax(dmax(tLLy, tRLy), sc2));
+  const double calfvenT = sqrt_pos_fast(dmax(dmax(tLRy, tRRy), sc2));
 #endif
 
   const double SAL = dmin0(ustar - calfvenL), SAR = dmax0(ustar + calfvenR);
