@@ -233,5 +233,6 @@ __global__ void __launch_bounds__(256) mhd2d_update_kernel(const MhdArgs a)
 
 #include "mhd_stage_r.cuh"
 #include "mhd_ru.cuh"
+#include "mhd_rui.cuh"
 #include "mhd_pet.cuh"
 #include "mhd_pet_tma.cuh"
