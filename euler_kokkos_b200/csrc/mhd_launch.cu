@@ -206,7 +206,7 @@ static cudaError_t launch_pet(Ctx& c, const MhdArgs& a)
       c.mhd_pet_tma_attr = true;
     }
     dim3 grid((g.isize - 3 + PT_TX - 1) / PT_TX, (g.jsize - 3 + PT_TY - 1) / PT_TY, 1); // cells 2 .. isize-2
-    const int zchunk = pick_pet_zchunk(nplanes, (long long)grid.x * grid.y, c.sm_count);
+    const int zchunk = pick_pet_zchunk(nplanes, (long long)grid.x * grid.y, (long long)PT_MINB * c.sm_count);
     grid.z = (nplanes + zchunk - 1) / zchunk;
     const int level = (a.Uin == c.U[0]) ? 0 : 1;
     mhd_pet_tma_kernel<<<grid, PT_TX * PT_TY, sizeof(PetTmaSmem), c.stream>>>(a, zchunk, c.umap[level]);

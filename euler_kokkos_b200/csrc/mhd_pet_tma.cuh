@@ -22,7 +22,17 @@
 
 namespace ek {
 
-constexpr int PT_TX = 32, PT_TY = 16;
+#ifndef EK_PET_TY
+#define EK_PET_TY 12 // tile rows (CTA = 32 x EK_PET_TY threads)
+#endif
+#ifndef EK_PET_NSTAGE
+#define EK_PET_NSTAGE 2 // TMA staging buffers (planes in flight ahead of the conversion); 2 needs EK_PET_TY <= 14 to fit 227 KB
+#endif
+#ifndef EK_PET_MINB
+#define EK_PET_MINB 1 // resident CTAs per SM the register budget is cut for
+#endif
+constexpr int PT_TX = 32, PT_TY = EK_PET_TY, PT_NS = EK_PET_NSTAGE, PT_MINB = EK_PET_MINB;
+static_assert(PT_NS == 1 || PT_NS == 2, "one or two staging buffers");
 constexpr int PT_BX = PT_TX + 2, PT_BY = PT_TY + 2, PT_BOX = PT_BX * PT_BY;  // 34 x 18 cells: tile + 1-cell ring
 constexpr int PT_TILES = (PT_BOX + 31) / 32;                                  // AoSoA tiles per plane of the ring
 constexpr int PT_QPLANE = PT_TILES * 8 * 32, PT_EPLANE = PT_TILES * 3 * 32;   // doubles
@@ -33,10 +43,10 @@ constexpr int PT_RPLANE = (PT_RBOX + 15) / 16 * 16;                           //
 constexpr unsigned PT_STAGE_BYTES = 9u * PT_RBOX * sizeof(double);            // 8 variables of plane k + C of plane k+1
 
 struct PetTmaSmem {
-  double raw[9][PT_RPLANE];  // TMA destination (128-byte aligned: first member)
+  double raw[PT_NS][9][PT_RPLANE];  // TMA destinations (128-byte aligned: first member)
   double q[3][PT_QPLANE];    // ring: r, p, u, v, w, A_face, B_face, C_face of planes p-1, p, p+1
   double e[2][PT_EPLANE];    // edge electric field of planes p, p+1
-  unsigned long long bar;    // mbarrier of the staging buffer
+  unsigned long long bar[PT_NS]; // mbarrier of each staging buffer
 };
 
 __device__ __forceinline__ unsigned smem_addr_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -101,7 +111,7 @@ struct PetRingIn {
   __device__ __forceinline__ double ek(int c) const { return e1p[tile_off<3>(b) + TL * c]; }
 };
 
-__global__ void __launch_bounds__(PT_TX* PT_TY, 1)
+__global__ void __launch_bounds__(PT_TX* PT_TY, PT_MINB)
   mhd_pet_tma_kernel(const MhdArgs a, const int zchunk, const __grid_constant__ CUtensorMap umap)
 {
   extern __shared__ __align__(1024) unsigned char pet_tma_raw[];
@@ -123,26 +133,37 @@ __global__ void __launch_bounds__(PT_TX* PT_TY, 1)
   static_assert(PT_BOX > NT && PT_BOX <= 2 * NT, "two passes over the box");
 
   if (t == 0) {
-    mbar_init(&sm.bar, 1);
+#pragma unroll
+    for (int b = 0; b < PT_NS; ++b)
+      mbar_init(&sm.bar[b], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  unsigned phase = 0;
-  // plane k (8 variables) + C of plane k+1 into the staging buffer; out-of-range parts of a box arrive as zeros
-  auto issue_plane = [&](int k) {
+  // The planes kbeg-1 .. kend are staged in order; the n-th of them goes through buffer n % PT_NS (parity of that
+  // buffer's mbarrier: (n / PT_NS) & 1).  A plane is issued as soon as the buffer it lands in has been converted.
+  int n_issued = 0, n_conv = 0;
+  // plane k (8 variables) + C of plane k+1 into a staging buffer; out-of-range parts of a box arrive as zeros
+  auto issue_next = [&]() {
+    const int k = kbeg - 1 + n_issued;
+    if (k > kend)
+      return; // never leave a load in flight at exit
+    const int b = n_issued % PT_NS;
+    ++n_issued;
     if (t == 0) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the buffer was read through the generic proxy
-      mbar_arrive_expect_tx(&sm.bar, PT_STAGE_BYTES);
+      mbar_arrive_expect_tx(&sm.bar[b], PT_STAGE_BYTES);
 #pragma unroll
       for (int v = 0; v < 8; ++v)
-        tma_load_4d(&sm.raw[v][0], &umap, &sm.bar, i0 - 2, j0 - 1, k, v);
-      tma_load_4d(&sm.raw[8][0], &umap, &sm.bar, i0 - 2, j0 - 1, k + 1, IC);
+        tma_load_4d(&sm.raw[b][v][0], &umap, &sm.bar[b], i0 - 2, j0 - 1, k, v);
+      tma_load_4d(&sm.raw[b][8][0], &umap, &sm.bar[b], i0 - 2, j0 - 1, k + 1, IC);
     }
   };
   // staged plane -> ring slot: primitives r, p, u, v, w + the three face fields of every box cell
   auto convert_to = [&](double* __restrict__ qs) {
-    mbar_wait(&sm.bar, phase);
-    phase ^= 1u;
+    const int sb = n_conv % PT_NS;
+    mbar_wait(&sm.bar[sb], (unsigned)(n_conv / PT_NS) & 1u);
+    ++n_conv;
+    const double(*__restrict__ raw)[PT_RPLANE] = sm.raw[sb];
 #pragma unroll
     for (int pass = 0; pass < 2; ++pass) {
       const int b = t + pass * NT;
@@ -152,8 +173,8 @@ __global__ void __launch_bounds__(PT_TX* PT_TY, 1)
         double u[8], q[8];
 #pragma unroll
         for (int v = 0; v < 8; ++v)
-          u[v] = sm.raw[v][o];
-        mhd_cons_to_prim(g, u, sm.raw[IA][o + 1], sm.raw[IB][o + PT_RX], sm.raw[8][o], q);
+          u[v] = raw[v][o];
+        mhd_cons_to_prim(g, u, raw[IA][o + 1], raw[IB][o + PT_RX], raw[8][o], q);
         double* __restrict__ qc = qs + tile_off<8>((unsigned)b);
 #pragma unroll
         for (int v = 0; v < 5; ++v)
@@ -198,18 +219,19 @@ __global__ void __launch_bounds__(PT_TX* PT_TY, 1)
 
   // ring slot of plane k: k % 3
   // prologue: planes kbeg-1, kbeg, kbeg+1 into the ring, E(kbeg); plane kbeg+2 left in flight
-  issue_plane(kbeg - 1);
+#pragma unroll
+  for (int b = 0; b < PT_NS; ++b)
+    issue_next();
   convert_to(sm.q[(kbeg - 1) % 3]);
   __syncthreads();
-  issue_plane(kbeg);
+  issue_next();
   convert_to(sm.q[kbeg % 3]);
   __syncthreads();
-  issue_plane(kbeg + 1);
+  issue_next();
   elec_plane(kbeg, sm.q[(kbeg - 1) % 3], sm.q[kbeg % 3], sm.e[kbeg & 1]);
   convert_to(sm.q[(kbeg + 1) % 3]);
   __syncthreads();
-  if (kbeg + 1 < kend)
-    issue_plane(kbeg + 2); // converted by the first iteration of the loop (never leave a load in flight at exit)
+  issue_next(); // plane kbeg+2 (+PT_NS-1): converted by the first iterations of the loop
 
   const int lx = t & (PT_TX - 1), ly = t / PT_TX;
   const unsigned bt = (unsigned)((1 + lx) + PT_BX * (1 + ly)); // this thread's cell inside the box
@@ -250,9 +272,8 @@ __global__ void __launch_bounds__(PT_TX* PT_TY, 1)
     if (p + 1 < kend) {
       __syncthreads();                      // every reader of ring plane p-1 is done
       convert_to(sm.q[(p + 2) % 3]);        // staged plane p+2 replaces plane p-1
-      __syncthreads();                      // ring plane p+2 visible, staging buffer free
-      if (p + 2 < kend)
-        issue_plane(p + 3);
+      __syncthreads();                      // ring plane p+2 visible, its staging buffer free
+      issue_next();                         // plane p+2+PT_NS
     }
   }
 }

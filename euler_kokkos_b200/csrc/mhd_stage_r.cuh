@@ -84,8 +84,11 @@ __device__ __forceinline__ void call_edge(const Grid& g, const double* __restric
   stg_edge_solver(g.gamma0, g.smallc, LL, RL, LR, RR, out);
 }
 
+#ifndef EK_MHD_R_MINB
+#define EK_MHD_R_MINB 4 // resident CTAs of 128 threads the register budget is cut for (128 registers)
+#endif
 template <int RS>
-__global__ void __launch_bounds__(128, 4) mhd_faces_edges_call_kernel(const MhdArgs a)
+__global__ void __launch_bounds__(128, EK_MHD_R_MINB) mhd_faces_edges_call_kernel(const MhdArgs a)
 {
   if (a.ts->finished)
     return;
