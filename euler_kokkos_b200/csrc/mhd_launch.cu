@@ -13,6 +13,12 @@
 #ifndef EK_MHD_U_PRE_DEFAULT
 #define EK_MHD_U_PRE_DEFAULT 0
 #endif
+#ifndef EK_MHD_R_PFL2_DEFAULT
+#define EK_MHD_R_PFL2_DEFAULT 3
+#endif
+#ifndef EK_MHD_U_PFL2_DEFAULT
+#define EK_MHD_U_PFL2_DEFAULT -1
+#endif
 #ifndef EK_MHD_RUI_DEFAULT
 #define EK_MHD_RUI_DEFAULT 0
 #endif
@@ -109,6 +115,13 @@ static void launch_update(const Ctx& c, dim3 grid, const MhdArgs& a)
       mhd_update_pre_kernel<true><<<grid, 256, 0, c.stream>>>(a);
     else
       mhd_update_pre_kernel<false><<<grid, 256, 0, c.stream>>>(a);
+    return;
+  }
+  if (a.pf_planes > 0) {
+    if (mhd_dt_folded(c))
+      mhd_update_kernel<true, true><<<grid, 256, 0, c.stream>>>(a);
+    else
+      mhd_update_kernel<false, true><<<grid, 256, 0, c.stream>>>(a);
     return;
   }
   if (mhd_dt_folded(c))
@@ -389,12 +402,22 @@ static cudaError_t launch_step(Ctx& c, const double* Uin, double* Uout, int part
     return e;
   if (part == 0 && use_rui(c))
     return launch_rui<RS>(c, a);
-  mhd_faces_edges_call_kernel<RS><<<blocks(a, 128), 128, 0, c.stream>>>(with_tall_ctas(a, "EK_MHD_R_TALL", EK_MHD_R_TALL_DEFAULT, 4));
+  {
+    MhdArgs ar = with_tall_ctas(a, "EK_MHD_R_TALL", EK_MHD_R_TALL_DEFAULT, 4);
+    ar.pf_planes = getenv("EK_MHD_R_PFL2") ? atoi(getenv("EK_MHD_R_PFL2")) : EK_MHD_R_PFL2_DEFAULT;
+    if (ar.cm.yc == 0)
+      ar.pf_planes = -1; // flat order: the next plane is a whole plane of CTAs away
+    mhd_faces_edges_call_kernel<RS><<<blocks(a, 128), 128, 0, c.stream>>>(ar);
+  }
   c.launches++;
   if (part == 1) {
     launch_update_ends(c, a);
   } else {
-    launch_update(c, dim3(blocks(a, 256)), with_tall_ctas(a, "EK_MHD_U_TALL", EK_MHD_U_TALL_DEFAULT, 8));
+    MhdArgs au = with_tall_ctas(a, "EK_MHD_U_TALL", EK_MHD_U_TALL_DEFAULT, 8);
+    au.pf_planes = getenv("EK_MHD_U_PFL2") ? atoi(getenv("EK_MHD_U_PFL2")) : EK_MHD_U_PFL2_DEFAULT;
+    if (au.cm.yc == 0 || au.pf_planes == 0)
+      au.pf_planes = -1;
+    launch_update(c, dim3(blocks(a, 256)), au);
     c.launches++;
   }
   return cudaGetLastError();

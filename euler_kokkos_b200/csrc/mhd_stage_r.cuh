@@ -93,11 +93,18 @@ __global__ void __launch_bounds__(128, EK_MHD_R_MINB) mhd_faces_edges_call_kerne
   if (a.ts->finished)
     return;
   MhdIdx x;
-  if (!mhd_cell_of_thread(a, x) || !mhd_stage_r_active(a.g, x))
+  if (!mhd_cell_of_thread(a, x))
     return;
   const Grid& g = a.g;
   const MhdWork w = mhd_work_split(a.work, g.sv);
   const double* __restrict__ S = w.S;
+  // L2 prefetch: this warp's lane 0 asks for the tile of S the warp pf_planes further along z will read first (one
+  // cp.async.bulk.prefetch.L2 of 9.7 KB: no registers, one instruction per warp), so that the first touch of a line of
+  // S is an L2 hit instead of a DRAM access (each of the six load batches of a thread waits for its slowest line)
+  if (a.pf_planes >= 0 && (threadIdx.x & 31) == 0 && x.k + a.pf_planes < g.ksize)
+    l2_prefetch_bulk(S + (size_t)((x.c + (unsigned)a.pf_planes * x.sk) >> 5) * (S_TOTAL * 32), S_TOTAL * 32 * sizeof(double));
+  if (!mhd_stage_r_active(g, x))
+    return;
   const unsigned c = x.c, sj = x.sj, sk = x.sk;
   const double* __restrict__ S000 = S + tile_off<S_TOTAL>(c);
   const double* __restrict__ S100 = S + tile_off<S_TOTAL>(c - 1);

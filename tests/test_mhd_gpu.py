@@ -117,6 +117,7 @@ def test_mhd3d_divb_and_conservation():
                                    {"EK_MHD_RUI": "1"}, {"EK_MHD_RUI": "1", "EK_MHD_DTFOLD": "0"}, {"EK_MHD_RUI": "1", "EK_MHD_YCHUNK": "0"},
                                    {"EK_MHD_RUI": "1", "EK_MHD_YCHUNK": "5", "EK_MHD_RUI_LAG": "1"},
                                    {"EK_MHD_RUI": "0", "EK_MHD_YCHUNK": "16"}, {"EK_MHD_U_PRE": "1"}, {"EK_MHD_U_PRE": "1", "EK_MHD_DTFOLD": "0"},
+                                   {"EK_MHD_R_PFL2": "3", "EK_MHD_U_PFL2": "2"}, {"EK_MHD_R_PFL2": "40", "EK_MHD_U_PFL2": "1", "EK_MHD_YCHUNK": "5"},
                                    {"EK_MHD_R_TALL": "1", "EK_MHD_U_TALL": "1"}, {"EK_MHD_R_TALL": "1", "EK_MHD_U_TALL": "1", "EK_MHD_YCHUNK": "5"},
                                    {"EK_MHD_R_TALL": "1", "EK_MHD_U_TALL": "1", "EK_MHD_U_PRE": "1", "EK_MHD_YCHUNK": "9"}])
 def test_mhd3d_kernel_variants_agree_with_the_oracle(knobs, monkeypatch):
