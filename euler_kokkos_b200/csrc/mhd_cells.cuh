@@ -97,10 +97,6 @@ struct MhdChunkMap {
   unsigned yc;     // rows per slab
   unsigned nchunk; // slabs
   unsigned span;   // threads per slab-plane: yc*isize rounded up to tiles + 1 tile
-  // "tall CTAs": the pw warps of a CTA take AoSoA tiles that lie (nearly) above each other -- tiles a, a + tpr,
-  // a + 2 tpr, ... with tpr = tiles per row -- instead of pw consecutive tiles of one row, so that the row j-1 one warp
-  // reads as its y neighbour is the row another warp of the same CTA (same SM, same L1) reads as its own.  pw = 0: off.
-  unsigned pw = 0, tpr = 1;
 };
 EK_HD MhdChunkMap mhd_chunk_map(const Grid& g, int yc)
 {
@@ -138,15 +134,7 @@ EK_HD bool mhd_chunk_cell(const Grid& g, const MhdChunkMap& m, unsigned t, MhdId
       return false;
     const unsigned r = t - ch * per_chunk;
     const unsigned k = r / m.span; // inside a slab: plane (slowest), then the cells of the slab-plane
-    unsigned o = r - k * m.span;
-    if (m.pw) {
-      const unsigned tile = o >> 5, bt = m.pw * m.tpr; // blocks of pw rows of tiles; the tail of the slab-plane keeps its order
-      const unsigned blk = tile / bt;
-      if ((blk + 1u) * bt <= (m.span >> 5)) {
-        const unsigned q = tile - blk * bt;
-        o = ((blk * bt + (q % m.pw) * m.tpr + q / m.pw) << 5) | (o & 31u);
-      }
-    }
+    const unsigned o = r - k * m.span;
     const unsigned j0 = ch * m.yc;
     const unsigned j1 = (j0 + m.yc < (unsigned)g.jsize) ? j0 + m.yc : (unsigned)g.jsize;
     const unsigned c0 = sj * j0 + sk * k;       // first cell of the slab-plane
@@ -664,7 +652,6 @@ EK_HD void mhd_stage_emfs(const Grid& g, const double* __restrict__ S, double* _
 // lower edges of the cell and of its +x, +y, +z, +x+y, +x+z, +y+z neighbours.  MhdUpdGlobal reads the F / EMF work
 // arrays (stage U as a kernel of its own); the fused R+U kernel reads its shared-memory planes (mhd_ru.cuh).
 struct MhdUpdGlobal {
-  static constexpr bool kPreloaded = false; // the old state U^n of the cell is read by mhd_update_core itself
   const double *F0, *Fi, *Fj, *Fk;           // tile pointers of the flux array at c, c+1, c+sj, c+sk
   const double *E0, *Ei, *Ej, *Ek, *Eij, *Eik, *Ejk; // ... of the EMF array
   EK_HD double fx0(int v) const { return F0[TL * v]; }
@@ -695,11 +682,7 @@ EK_HD double mhd_update_core(const Grid& g, const double* __restrict__ Uin, doub
   double un[8];
 #pragma unroll
   for (int v = 0; v < 5; ++v) {
-    double u;
-    if constexpr (SRC::kPreloaded)
-      u = P.u(v); // a source that has already loaded U^n of the cell (and of its three upper faces) next to the fluxes
-    else
-      u = Uc[sv * v];
+    double u = Uc[sv * v];
     u += P.fx0(v) * dtdx;
     u -= P.fxi(v) * dtdx;
     u += P.fy0(v) * dtdy;
@@ -709,12 +692,7 @@ EK_HD double mhd_update_core(const Grid& g, const double* __restrict__ Uin, doub
     Oc[sv * v] = u;
     un[v] = u;
   }
-  double A, B, C;
-  if constexpr (SRC::kPreloaded) {
-    A = P.u(IA); B = P.u(IB); C = P.u(IC);
-  } else {
-    A = Uc[sv * IA]; B = Uc[sv * IB]; C = Uc[sv * IC];
-  }
+  double A = Uc[sv * IA], B = Uc[sv * IB], C = Uc[sv * IC];
   const double ex = P.e0(0), ey = P.e0(1), ez = P.e0(2);
   A += (P.ej(2) - ez) * dtdy;
   B -= (P.ei(2) - ez) * dtdx;
@@ -731,12 +709,7 @@ EK_HD double mhd_update_core(const Grid& g, const double* __restrict__ Uin, doub
     return 0.0;
   // the new field on the three upper faces = lower faces of the +x / +y / +z neighbours
   const unsigned sj = x.sj, sk = x.sk;
-  double A1, B1, C1;
-  if constexpr (SRC::kPreloaded) {
-    A1 = P.u(8); B1 = P.u(9); C1 = P.u(10);
-  } else {
-    A1 = Uc[sv * IA + 1]; B1 = Uc[sv * IB + sj]; C1 = Uc[sv * IC + sk];
-  }
+  double A1 = Uc[sv * IA + 1], B1 = Uc[sv * IB + sj], C1 = Uc[sv * IC + sk];
   A1 += (P.eij(2) - P.ei(2)) * dtdy;
   A1 -= (P.eik(1) - P.ei(1)) * dtdz;
   B1 -= (P.eij(2) - P.ej(2)) * dtdx;

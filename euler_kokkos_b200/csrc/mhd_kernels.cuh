@@ -17,7 +17,7 @@ struct MhdArgs {
   unsigned t0 = 0; // offset added to the linear thread index (launches restricted to a range of planes / of y-slabs)
   unsigned t1 = 0xffffffffu; // one past the last linear thread index this launch may take
   int upd_klo = 0, upd_khi = 1 << 30; // planes [upd_klo, upd_khi) the update kernel may write
-  int pf_planes = -1; // (-1: off) stages R / U: every warp asks L2 for the tile(s) the warp this many planes further along z will read
+  int pf_planes = -1; // stage R: every warp asks L2 for the tile of S the warp this many planes further along z will read (-1: off)
 };
 
 // cp.async.bulk.prefetch.L2 (sm_90+): one instruction of one lane brings a contiguous block (a whole AoSoA tile) into L2
@@ -100,7 +100,7 @@ __device__ __forceinline__ void mhd_block_max_invdt(double m, TimeState* ts)
 #ifndef EK_MHD_U_MINB
 #define EK_MHD_U_MINB 5 // resident CTAs of 256 threads the register budget is cut for (measured: 4 and 6 are slower)
 #endif
-template <bool INVDT, bool PF = false>
+template <bool INVDT>
 __global__ void __launch_bounds__(256, EK_MHD_U_MINB) mhd_update_kernel(const MhdArgs a)
 {
   if (a.ts->finished)
@@ -109,18 +109,7 @@ __global__ void __launch_bounds__(256, EK_MHD_U_MINB) mhd_update_kernel(const Mh
   const double dt = a.ts->dt;
   MhdIdx x;
   double m = 0.0;
-  const bool ok = mhd_cell_of_thread(a, x);
-  if (PF && ok && (threadIdx.x & 31) == 0 && x.k + a.pf_planes < a.g.ksize - 1) {
-    // the warp that will update this tile's column pf_planes further up: its fluxes, EMFs and old state into L2 now
-    const unsigned cp = x.c + (unsigned)a.pf_planes * x.sk;
-    l2_prefetch_bulk(w.F + (size_t)(cp >> 5) * (15 * 32), 15 * 32 * sizeof(double));
-    l2_prefetch_bulk(w.EMF + (size_t)(cp >> 5) * (3 * 32), 3 * 32 * sizeof(double));
-    const double* up = a.Uin + (cp & ~1u); // 16-byte aligned
-#pragma unroll
-    for (int v = 0; v < 8; ++v)
-      l2_prefetch_bulk(up + a.g.sv * v, 32 * sizeof(double));
-  }
-  if (ok && x.k >= a.upd_klo && x.k < a.upd_khi)
+  if (mhd_cell_of_thread(a, x) && x.k >= a.upd_klo && x.k < a.upd_khi)
     m = mhd_stage_update_t<INVDT>(a.g, a.Uin, w.F, w.EMF, a.Uout, dt / a.g.dx, dt / a.g.dy, dt / a.g.dz, x);
   if constexpr (INVDT)
     mhd_block_max_invdt(m, a.ts);
@@ -251,6 +240,5 @@ __global__ void __launch_bounds__(256) mhd2d_update_kernel(const MhdArgs a)
 
 #include "mhd_stage_r.cuh"
 #include "mhd_ru.cuh"
-#include "mhd_rui.cuh"
 #include "mhd_pet.cuh"
 #include "mhd_pet_tma.cuh"

@@ -4,40 +4,18 @@
 #include "ek_internal.h"
 #include "mhd_kernels.cuh"
 
-#ifndef EK_MHD_R_TALL_DEFAULT
-#define EK_MHD_R_TALL_DEFAULT 0
-#endif
-#ifndef EK_MHD_U_TALL_DEFAULT
-#define EK_MHD_U_TALL_DEFAULT 0
-#endif
-#ifndef EK_MHD_U_PRE_DEFAULT
-#define EK_MHD_U_PRE_DEFAULT 0
-#endif
 #ifndef EK_MHD_R_PFL2_DEFAULT
-#define EK_MHD_R_PFL2_DEFAULT 3
-#endif
-#ifndef EK_MHD_U_PFL2_DEFAULT
-#define EK_MHD_U_PFL2_DEFAULT -1
-#endif
-#ifndef EK_MHD_RUI_DEFAULT
-#define EK_MHD_RUI_DEFAULT 0
+#define EK_MHD_R_PFL2_DEFAULT 2 // stage R: lead (in planes) of the bulk L2 prefetch of S; -1 = off
 #endif
 
 namespace ek {
 
-// the work arrays, followed (3-D) by the completion counters of the interleaved R+U kernel: one per slab-plane, at most
-// jsize * ksize of them (mhd_rui.cuh)
-static size_t mhd_work_array_bytes(const Grid& g)
+size_t mhd_work_bytes(const Grid& g)
 {
   return (size_t)(g.ksize > 1 ? W3_DEVICE : W2_TOTAL) * (size_t)mhd_padded_cells(g.sv) * sizeof(double);
 }
-size_t mhd_work_bytes(const Grid& g)
-{
-  const size_t flags = (g.ksize > 1) ? (((size_t)g.jsize * (size_t)g.ksize * sizeof(unsigned) + 255) & ~(size_t)255) : 0;
-  return mhd_work_array_bytes(g) + flags;
-}
 
-// 4-D tensor maps (x, y, z, variable) over both time levels, box = 36 x 19 x 1 x 1 doubles, no swizzle, zero fill
+// 4-D tensor maps (x, y, z, variable) over both time levels, box = 36 x (tile rows + 3) x 1 x 1 doubles, no swizzle, zero fill
 // outside the array.  The encoder is a driver entry point: looked up at run time, libcuda is not linked.
 bool mhd_make_tensor_maps(Ctx& c)
 {
@@ -85,20 +63,6 @@ static MhdArgs make_args(Ctx& c, const double* Uin, double* Uout)
   return a;
 }
 
-// tall CTAs (mhd_cells.cuh): warps per CTA stacked along y for a stencil stage launched with `warps` warps per CTA
-static MhdArgs with_tall_ctas(const MhdArgs& a0, const char* env, int dflt, int warps)
-{
-  MhdArgs a = a0;
-  const int on = getenv(env) ? atoi(getenv(env)) : dflt;
-  if (on && a.cm.yc >= (unsigned)warps) {
-    a.cm.pw = (unsigned)warps;
-    a.cm.tpr = ((unsigned)a.g.isize + 16u) / 32u;
-    if (a.cm.tpr == 0)
-      a.cm.tpr = 1;
-  }
-  return a;
-}
-
 // CFL reduction of the next step inside the update kernel (3-D); EK_MHD_DTFOLD=0 restores the stand-alone pass
 bool mhd_dt_folded(const Ctx& c)
 {
@@ -108,22 +72,6 @@ bool mhd_dt_folded(const Ctx& c)
 
 static void launch_update(const Ctx& c, dim3 grid, const MhdArgs& a)
 {
-  // EK_MHD_U_PRE=1: every operand of a cell loaded up front (mhd_update_pre_kernel, mhd_rui.cuh)
-  const int pre = getenv("EK_MHD_U_PRE") ? atoi(getenv("EK_MHD_U_PRE")) : EK_MHD_U_PRE_DEFAULT;
-  if (pre && c.p.dim == 3) {
-    if (mhd_dt_folded(c))
-      mhd_update_pre_kernel<true><<<grid, 256, 0, c.stream>>>(a);
-    else
-      mhd_update_pre_kernel<false><<<grid, 256, 0, c.stream>>>(a);
-    return;
-  }
-  if (a.pf_planes > 0) {
-    if (mhd_dt_folded(c))
-      mhd_update_kernel<true, true><<<grid, 256, 0, c.stream>>>(a);
-    else
-      mhd_update_kernel<false, true><<<grid, 256, 0, c.stream>>>(a);
-    return;
-  }
   if (mhd_dt_folded(c))
     mhd_update_kernel<true><<<grid, 256, 0, c.stream>>>(a);
   else
@@ -295,51 +243,7 @@ static bool use_ru(const Ctx& c)
   const int v = getenv("EK_MHD_RU") ? atoi(getenv("EK_MHD_RU")) : 0;
   return v != 0 && c.p.dim == 3;
 }
-// EK_MHD_RUI=1: stages R and U interleaved by CTA role inside one launch (mhd_rui.cuh); the update of the end planes
-// cannot be taken first then, so the z-halo exchange follows the step instead of running beside it
-static bool use_rui(const Ctx& c)
-{
-  const int v = getenv("EK_MHD_RUI") ? atoi(getenv("EK_MHD_RUI")) : EK_MHD_RUI_DEFAULT;
-  return v != 0 && c.p.dim == 3 && !use_ru(c);
-}
-bool mhd_z_splittable(const Ctx& c)
-{
-  if (use_ru(c))
-    return ru_plan(c, true).splittable;
-  if (use_rui(c))
-    return false;
-  return c.p.nz >= 2 * c.p.ghost;
-}
-
-template <int RS>
-static cudaError_t launch_rui(Ctx& c, const MhdArgs& a0)
-{
-  const Grid& g = c.g;
-  MhdRuiArgs ra;
-  ra.a = a0;
-  if (ra.a.cm.yc == 0) // the role interleaving needs slabs: a flat order is one slab of all rows
-    ra.a.cm = mhd_chunk_map(g, g.jsize);
-  ra.a.cm.span = (ra.a.cm.span + RUI_THREADS - 1) / RUI_THREADS * RUI_THREADS;
-  const int lag = getenv("EK_MHD_RUI_LAG") ? atoi(getenv("EK_MHD_RUI_LAG")) : 8;
-  ra.lag = (unsigned)(lag < 1 ? 1 : lag);
-  ra.nR = ra.a.cm.span / RUI_THREADS;
-  ra.nU = (ra.a.cm.span + RUI_THREADS * RUI_UC - 1) / (RUI_THREADS * RUI_UC);
-  ra.ngroups = (unsigned)g.ksize + ra.lag;
-  ra.flags = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(c.work) + mhd_work_array_bytes(g));
-  const size_t nflags = (size_t)ra.a.cm.nchunk * (size_t)g.ksize;
-  cudaError_t e = cudaMemsetAsync(ra.flags, 0, nflags * sizeof(unsigned), c.stream);
-  if (e != cudaSuccess)
-    return e;
-  const unsigned long long ctas = (unsigned long long)ra.a.cm.nchunk * ra.ngroups * (ra.nR + ra.nU);
-  if (ctas > 0x7fffffffull)
-    return cudaErrorInvalidValue;
-  if (mhd_dt_folded(c))
-    mhd_rui_kernel<RS, true><<<(unsigned)ctas, RUI_THREADS, 0, c.stream>>>(ra);
-  else
-    mhd_rui_kernel<RS, false><<<(unsigned)ctas, RUI_THREADS, 0, c.stream>>>(ra);
-  c.launches++;
-  return cudaGetLastError();
-}
+bool mhd_z_splittable(const Ctx& c) { return use_ru(c) ? ru_plan(c, true).splittable : (c.p.nz >= 2 * c.p.ghost); }
 
 // part: 0 = every chunk, 1 = the two end chunks, 2 = the middle chunks
 template <int RS>
@@ -400,24 +304,20 @@ static cudaError_t launch_step(Ctx& c, const double* Uin, double* Uout, int part
   cudaError_t e = launch_pet(c, a);
   if (e != cudaSuccess)
     return e;
-  if (part == 0 && use_rui(c))
-    return launch_rui<RS>(c, a);
   {
-    MhdArgs ar = with_tall_ctas(a, "EK_MHD_R_TALL", EK_MHD_R_TALL_DEFAULT, 4);
+    // EK_MHD_R_PFL2: every warp of stage R asks L2 for the S tile of the warp this many planes further along z
+    // (mhd_stage_r.cuh); meaningful with the y-chunked launch order only (flat: the next plane is a whole plane of CTAs away)
+    MhdArgs ar = a;
     ar.pf_planes = getenv("EK_MHD_R_PFL2") ? atoi(getenv("EK_MHD_R_PFL2")) : EK_MHD_R_PFL2_DEFAULT;
     if (ar.cm.yc == 0)
-      ar.pf_planes = -1; // flat order: the next plane is a whole plane of CTAs away
+      ar.pf_planes = -1;
     mhd_faces_edges_call_kernel<RS><<<blocks(a, 128), 128, 0, c.stream>>>(ar);
   }
   c.launches++;
   if (part == 1) {
     launch_update_ends(c, a);
   } else {
-    MhdArgs au = with_tall_ctas(a, "EK_MHD_U_TALL", EK_MHD_U_TALL_DEFAULT, 8);
-    au.pf_planes = getenv("EK_MHD_U_PFL2") ? atoi(getenv("EK_MHD_U_PFL2")) : EK_MHD_U_PFL2_DEFAULT;
-    if (au.cm.yc == 0 || au.pf_planes == 0)
-      au.pf_planes = -1;
-    launch_update(c, dim3(blocks(a, 256)), au);
+    launch_update(c, dim3(blocks(a, 256)), a);
     c.launches++;
   }
   return cudaGetLastError();

@@ -5,17 +5,19 @@
 // global loads per thread and plane (11 per converted cell, 18 + 9 face-field values for the predictor and the edge
 // field); ncu at 512^3: 4.4 long-scoreboard stall cycles per issued instruction at 16 warps per SM, L1 hit rate 20 %
 // (the 214 KB of shared memory leave ~30 KB of L1), FP64 pipe 22 %, DRAM 40 %.  Here
-//   * one elected thread issues, per plane, nine 4-D box loads (36 x 19 cells of one variable each: the 8 variables of
-//     the plane and the field component C of the plane above -- the cell-centred C needs the upper z face) into a
-//     staging buffer: 49 KB in flight while the CTA works on the two planes before it;
+//   * one elected thread issues, per plane, nine 4-D box loads (36 x 15 cells of one variable each: the 8 variables of
+//     the plane and the field component C of the plane above -- the cell-centred C needs the upper z face) into one of
+//     TWO staging buffers: two planes (2 x 39 KB) in flight while the CTA works on the planes before them;
 //   * the ring of three planes in shared memory keeps, per cell, r, p, u, v, w and the three FACE fields A, B, C --
 //     everything the predictor and the edge field read (cell-centred B = mean of two faces, formed on the fly with
 //     the expression cons->prim uses), so their 27 face-field loads are shared-memory reads of data that is there anyway;
-//   * a CTA is 32 x 16 cells (512 threads, one per SM; same 16 warps per SM as before) => box 34 x 18: 19 % of the
-//     converted cells are halo instead of 33 %.
+//   * a CTA is 32 x 12 cells (384 threads, one per SM) => box 34 x 14.  The first TMA version used 32 x 16 cells = 512
+//     threads, which caps the kernel at 128 registers per thread; the predictor wants ~168 (ptxas with the cap lifted),
+//     and with 384 threads it gets them: 14.9 -> 11.9 ms at 512^3 (tiles of 16 / 14 / 12 / 10 / 8 rows measured:
+//     50.8 / 49.7 / 48.7-49.0 / 49.2 / 49.7 ms per step; two CTAs of 8 rows per SM at 128 registers: 52.7).
 // Per plane: E(p+1) from the ring | barrier | predictor of plane p -> S | barrier | staged plane p+2 -> ring slot of
-// plane p-1 | barrier | TMA of plane p+3.  The per-cell arithmetic is the code of mhd_cells.cuh (mhd_cons_to_prim,
-// mhd_elec_core, mhd_trace_core).
+// plane p-1 | barrier | TMA of plane p+4 into the buffer plane p+2 came from.  The per-cell arithmetic is the code of
+// mhd_cells.cuh (mhd_cons_to_prim, mhd_elec_core, mhd_trace_core).
 #pragma once
 #include <cuda.h> // CUtensorMap (type only: the encoder is looked up at run time, ek_api.cu)
 #include "mhd_cells.cuh"
@@ -37,7 +39,7 @@ constexpr int PT_BX = PT_TX + 2, PT_BY = PT_TY + 2, PT_BOX = PT_BX * PT_BY;  // 
 constexpr int PT_TILES = (PT_BOX + 31) / 32;                                  // AoSoA tiles per plane of the ring
 constexpr int PT_QPLANE = PT_TILES * 8 * 32, PT_EPLANE = PT_TILES * 3 * 32;   // doubles
 constexpr int PT_RX = 36, PT_RY = PT_BY + 1;                                  // staged box: columns i0-2 .. i0+33 (the box start must be
-                                                                              // 16-byte aligned: an odd start column is an illegal instruction), 19 rows
+                                                                              // 16-byte aligned: an odd start column is an illegal instruction), PT_TY+3 rows
 constexpr int PT_RBOX = PT_RX * PT_RY;                                        // doubles per staged variable (one TMA box)
 constexpr int PT_RPLANE = (PT_RBOX + 15) / 16 * 16;                           // ... padded: every box lands 128-byte aligned
 constexpr unsigned PT_STAGE_BYTES = 9u * PT_RBOX * sizeof(double);            // 8 variables of plane k + C of plane k+1

@@ -29,7 +29,6 @@ struct RuSmem {
 
 // flux / EMF sources of mhd_update_core for the cell of thread slot t: plane k-1 in `lo`, plane k in `hi`
 struct MhdUpdSmem {
-  static constexpr bool kPreloaded = false;
   const double* lo;
   const double* hi;
   int t;

@@ -114,14 +114,11 @@ def test_mhd3d_divb_and_conservation():
 
 @pytest.mark.parametrize("knobs", [{"EK_MHD_RU": "0", "EK_MHD_YCHUNK": "0"}, {"EK_MHD_RU": "0", "EK_MHD_YCHUNK": "5"}, {"EK_MHD_RU": "0"},
                                    {"EK_MHD_RU": "0", "EK_MHD_DTFOLD": "0"}, {"EK_MHD_RU": "1"}, {"EK_MHD_RU": "1", "EK_MHD_DTFOLD": "0"},
-                                   {"EK_MHD_RUI": "1"}, {"EK_MHD_RUI": "1", "EK_MHD_DTFOLD": "0"}, {"EK_MHD_RUI": "1", "EK_MHD_YCHUNK": "0"},
-                                   {"EK_MHD_RUI": "1", "EK_MHD_YCHUNK": "5", "EK_MHD_RUI_LAG": "1"},
-                                   {"EK_MHD_RUI": "0", "EK_MHD_YCHUNK": "16"}, {"EK_MHD_U_PRE": "1"}, {"EK_MHD_U_PRE": "1", "EK_MHD_DTFOLD": "0"},
-                                   {"EK_MHD_R_PFL2": "3", "EK_MHD_U_PFL2": "2"}, {"EK_MHD_R_PFL2": "40", "EK_MHD_U_PFL2": "1", "EK_MHD_YCHUNK": "5"},
-                                   {"EK_MHD_R_TALL": "1", "EK_MHD_U_TALL": "1"}, {"EK_MHD_R_TALL": "1", "EK_MHD_U_TALL": "1", "EK_MHD_YCHUNK": "5"},
-                                   {"EK_MHD_R_TALL": "1", "EK_MHD_U_TALL": "1", "EK_MHD_U_PRE": "1", "EK_MHD_YCHUNK": "9"}])
+                                   {"EK_MHD_R_PFL2": "-1"}, {"EK_MHD_R_PFL2": "0"}, {"EK_MHD_R_PFL2": "3", "EK_MHD_YCHUNK": "16"},
+                                   {"EK_MHD_R_PFL2": "40", "EK_MHD_YCHUNK": "5"}])
 def test_mhd3d_kernel_variants_agree_with_the_oracle(knobs, monkeypatch):
-    """the fused R+U kernel and the two-kernel form (with its launch orders: flat, y-chunked) and both placements of the CFL reduction are held to the same
+    """the fused R+U kernel and the two-kernel form (with its launch orders: flat, y-chunked; with the bulk L2 prefetch of stage R
+    off, at leads of 0 / 3 planes and at a lead longer than the grid) and both placements of the CFL reduction are held to the same
     one-step tolerance (the variants that lost in round 1 -- cp.async-staged and fully inlined stage R, z-grouped order,
     L2 prefetches, three-kernel P/E/T, the slab-pipelined launch -- are gone; DESIGN.md keeps their measurements)"""
     for k, v in knobs.items():
@@ -141,36 +138,6 @@ def test_mhd3d_fused_flux_update_kernel(n, bc, ru, monkeypatch):
     monkeypatch.setenv("EK_MHD_RU", ru)
     p = util.make_params(dim=3, mhd=True, n=n, riemann="hlld", bc=bc, smallr=1e-8, smallc=1e-8, box=((0, 1.0), (0, 0.7), (0, 0.4)))
     _check_steps(p, util.random_hydro_state(p, seed=13, mach=2.0), 2)
-
-
-@pytest.mark.parametrize("lag", ["8", "1", "3"])
-@pytest.mark.parametrize("n,bc,ychunk", [((31, 15, 9), (3, 3, 1, 2, 2, 1), "16"), ((62, 30, 4), (1, 2, 3, 3, 1, 1), "4"),
-                                         ((63, 31, 17), (3, 3, 3, 3, 3, 3), "1"), ((33, 46, 3), (2, 1, 1, 1, 3, 3), "16"),
-                                         ((96, 20, 26), (1, 1, 1, 1, 1, 1), "7"), ((200, 40, 12), (3, 3, 3, 3, 3, 3), "16")])
-def test_mhd3d_interleaved_flux_update_kernel_is_bitwise_the_two_kernel_form(n, bc, ychunk, lag, monkeypatch):
-    """Stages R and U interleaved by CTA role inside one launch (mhd_rui.cuh: stage-U CTAs of slab-plane g-LAG between
-    the stage-R CTAs of slab-plane g, completion counters per slab-plane) run the same arithmetic as the two-kernel form:
-    after a device-resident run the states, the time and the last dt are bitwise equal; and the step agrees with the
-    oracle.  Slabs of 1, 4, 7, 16 rows (one slab, several slabs, a last slab of one row), lags of 1, 3, 8 planes (a
-    lag of 1 makes the stage-U CTAs really wait on the counters), every boundary type."""
-    from euler_kokkos_b200 import capi
-
-    monkeypatch.setenv("EK_MHD_YCHUNK", ychunk)
-    monkeypatch.setenv("EK_MHD_RUI_LAG", lag)
-    p = util.make_params(dim=3, mhd=True, n=n, riemann="hlld", bc=bc, smallr=1e-8, smallc=1e-8, box=((0, 1.0), (0, 0.7), (0, 0.4)))
-    U0 = util.random_hydro_state(p, seed=17, mach=2.0)
-    out = {}
-    for rui in ("0", "1"):
-        monkeypatch.setenv("EK_MHD_RUI", rui)
-        ctx = capi.Context(p)
-        ctx.upload(U0)
-        t, dt, nst = ctx.run(5)
-        out[rui] = (ctx.download(), t, dt, nst)
-        ctx.close()
-    assert out["0"][1:] == out["1"][1:], (out["0"][1:], out["1"][1:])
-    assert np.array_equal(out["0"][0], out["1"][0])
-    monkeypatch.setenv("EK_MHD_RUI", "1")
-    _check_steps(p, U0, 1)
 
 
 @pytest.mark.parametrize("tma", ["1", "0"])

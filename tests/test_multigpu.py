@@ -88,16 +88,14 @@ def test_hydro3d_two_slabs_periodic_z_with_gravity(tmp_path):
               16, 2, 6, tmp_path, 1e-13)
 
 
-@pytest.mark.parametrize("ru", ["0", "1", "rui"])
+@pytest.mark.parametrize("ru", ["0", "1"])
 @pytest.mark.parametrize("overlap", ["1", "0"])
 def test_mhd3d_two_slabs_periodic_match_single_domain(tmp_path, monkeypatch, overlap, ru):
     """overlap=1: the update stage does the END planes first (ru=1, the fused R+U kernel: the end z-chunks) and their
-    exchange runs beside the update of the rest; ru=rui: stages R and U interleaved in one launch (the exchange follows
-    the step)"""
+    exchange runs beside the update of the rest"""
     monkeypatch.setenv("EK_HALO_OVERLAP", overlap)
-    monkeypatch.setenv("EK_MHD_RU", "1" if ru == "1" else "0")
-    monkeypatch.setenv("EK_MHD_RUI", "1" if ru == "rui" else "0")
-    _run_case("test_mhd_orszag_tang_3D.ini", {"mesh.nx": 32, "mesh.ny": 32}, 30 if ru == "1" else 12, 2, 8, tmp_path, 1e-13)
+    monkeypatch.setenv("EK_MHD_RU", ru)
+    _run_case("test_mhd_orszag_tang_3D.ini", {"mesh.nx": 32, "mesh.ny": 32}, 12 if ru == "0" else 30, 2, 8, tmp_path, 1e-13)
 
 
 # ---- mx x my x mz decompositions ([mpi] section of the ini, HydroParams.cpp:186-320): packed x / y halos ------------
