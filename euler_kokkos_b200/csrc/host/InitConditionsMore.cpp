@@ -11,14 +11,22 @@
 //          kelvin_helmholtz   MHDInitFunctors2D.h:484-676, MHDInitFunctors3D.h:560-765
 //          rotor              MHDInitFunctors2D.h:678-803, MHDInitFunctors3D.h:767-897, RotorParams.h
 //          field_loop         MHDInitFunctors2D.h:805-1036, MHDInitFunctors3D.h:899-1164, FieldLoopParams.h
-// Known, documented departures (the reference's behaviour is not reproducible there):
-//   * KH "perturbation_rand": the reference draws from Kokkos::Random_XorShift64_Pool, whose stream depends on the
-//     backend, the thread count and the iteration-to-thread map; here a counter-based generator keyed on
-//     (seed, global cell index) gives a perturbation that is identical for every decomposition and thread count.
+// KH "perturbation_rand": the reference draws from Kokkos::Random_XorShift64_Pool inside an MDRangePolicy loop, so its
+// stream depends on the back-end, the thread count and the iteration-to-thread map.  The stream of its OpenMP back-end
+// is deterministic for a given thread count and is reproduced here bit for bit (KokkosPoolStream below: the pool's
+// seeding, the xorshift64* generator, the host tiling of MDRangePolicy and the schedule(static,1) tile-to-thread map;
+// tests/test_oracle_golden.py::test_kh_random_perturbation_matches_the_reference_stream against dumps of the reference
+// binary run with 1, 3 and 4 threads).  Thread count: $EK_KH_RAND_THREADS, else $OMP_NUM_THREADS (what the reference
+// binary obeys), else 1; per-rank seed = rand_seed * (rank + 1) as KHParams.h:60-70.  "[KH] rand_generator=hash" selects
+// the counter-based generator instead (keyed on (seed, global cell index): identical for every decomposition and
+// thread count, which the reference's is not).  The stream of the reference's Cuda back-end (state picked by GPU
+// thread / block index behind atomic locks) is not reproducible and is not attempted.
+// Known, documented departure:
 //   * MHD blast: the reference never assigns blast_bz_in / blast_bz_out (BlastParams.h:56-62 assigns by_* twice and
 //     leaves bz_* uninitialised); Bz = 0 here.
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <iostream>
 #include <vector>
 
@@ -52,9 +60,90 @@ inline uint64_t global_cell(const Geo& g, const HydroParams& p, int i, int j, in
   return (uint64_t)(I + gx * (J + gy * K));
 }
 
+// ---- Kokkos::Random_XorShift64_Pool as consumed by a host MDRangePolicy loop ------------------------------------
+// external/kokkos/algorithms/src/Kokkos_Random.hpp:750-1000 (generator :769-785, :859; pool seeding :958-973; state of a
+// thread = pool entry omp_get_thread_num(), :621-630), external/kokkos/core/src/KokkosExp_MDRangePolicy.hpp:140-175,
+// 383-450 (host tiles: 2 in every rank but the innermost of the iteration direction, which takes its full range;
+// Iterate::Right on host back-ends), impl/KokkosExp_Host_IterateTile.hpp:1567-1592 (tile index -> offsets, last rank
+// fastest), OpenMP/Kokkos_OpenMP_Parallel_For.hpp:181-186 (schedule(static, 1) over the tiles).
+struct KokkosXorShift64 {
+  uint64_t s;
+  explicit KokkosXorShift64(uint64_t state) : s(state == 0 ? 1318319ull : state) {}
+  void step()
+  {
+    s ^= s >> 12;
+    s ^= s << 25;
+    s ^= s >> 27;
+  }
+  uint32_t urand()
+  {
+    step();
+    return (uint32_t)(((s * 2685821657736338717ull) >> 16) & 0xffffffffull);
+  }
+  int rand() { return (int)(urand() / 2); }
+  uint64_t urand64()
+  {
+    step();
+    return s * 2685821657736338717ull - 1;
+  }
+  double drand() { return urand64() / (double)UINT64_MAX; }
+};
+
+// ndraw uniform numbers per cell of the ghosted box, in the order the reference's OpenMP run with `threads` threads
+// draws them: value d of cell (i,j,k) at r[ndraw * g.at(i,j,k) + d]
+struct KokkosPoolStream {
+  std::vector<double> r;
+  int ndraw;
+  KokkosPoolStream(const Geo& g, uint64_t seed, int threads, int ndraw_) : r((size_t)ndraw_ * g.sv), ndraw(ndraw_)
+  {
+    if (seed == 0)
+      seed = 1318319ull;
+    if (threads < 1)
+      threads = 1;
+    std::vector<KokkosXorShift64> state;
+    {
+      KokkosXorShift64 gen(seed);
+      for (int i = 0; i < 17; ++i)
+        gen.rand();
+      for (int t = 0; t < threads; ++t) {
+        const uint64_t n1 = (uint64_t)gen.rand(), n2 = (uint64_t)gen.rand(), n3 = (uint64_t)gen.rand(), n4 = (uint64_t)gen.rand();
+        state.emplace_back(((n1 & 0xffff) << 0) | ((n2 & 0xffff) << 16) | ((n3 & 0xffff) << 32) | ((n4 & 0xffff) << 48));
+      }
+    }
+    // tiles: 2 x jsize (2-D), 2 x 2 x ksize (3-D); tile index = ti (2-D), ti * ntj + tj (3-D); tile w -> thread w % T,
+    // every thread takes its tiles in increasing order; inside a tile the last index runs fastest
+    const int nti = (g.isize + 1) / 2;
+    const int ntj = (g.dim == 3) ? (g.jsize + 1) / 2 : 1;
+    const int tj = (g.dim == 3) ? 2 : g.jsize;
+    for (int w = 0; w < nti * ntj; ++w) {
+      KokkosXorShift64& gen = state[(size_t)(w % threads)];
+      const int i0 = (w / ntj) * 2, j0 = (w % ntj) * tj;
+      for (int i = i0; i < i0 + 2 && i < g.isize; ++i)
+        for (int j = j0; j < j0 + tj && j < g.jsize; ++j)
+          for (int k = 0; k < g.ksize; ++k) {
+            double* o = r.data() + (size_t)ndraw * g.at(i, j, k);
+            for (int d = 0; d < ndraw; ++d)
+              o[d] = gen.drand(); // get_state / free_state around every cell hand the same state back
+          }
+    }
+  }
+  double operator()(const Geo& g, int i, int j, int k, int d) const { return r[(size_t)ndraw * g.at(i, j, k) + d]; }
+};
+
+inline int kh_rand_threads()
+{
+  for (const char* name : { "EK_KH_RAND_THREADS", "OMP_NUM_THREADS" }) {
+    const char* v = std::getenv(name);
+    if (v && std::atoi(v) > 0)
+      return std::atoi(v);
+  }
+  return 1;
+}
+
 struct KH {
   double d_in, d_out, pressure, vflow_in, vflow_out, amplitude, w0 = 0.0, delta = 0.0;
   bool p_sine, p_sine_rob, p_rand;
+  bool hash_rng = false; // [KH] rand_generator=hash: the counter-based generator instead of the reference's stream
   long seed = 0;
   int mode = 0;
   explicit KH(const ConfigMap& cm)
@@ -67,14 +156,36 @@ struct KH {
     p_rand = cm.getBool("KH", "perturbation_rand", false);
     vflow_in = cm.getFloat("KH", "vflow_in", -0.5);
     vflow_out = cm.getFloat("KH", "vflow_out", 0.5);
-    if (p_rand)
+    if (p_rand) {
       seed = cm.getInteger("KH", "rand_seed", 12);
+      hash_rng = cm.getString("KH", "rand_generator", "kokkos") == "hash";
+    }
     amplitude = cm.getFloat("KH", "amplitude", 0.1);
     if (p_sine_rob || p_sine) {
       mode = (int)cm.getInteger("KH", "mode", 2);
       w0 = cm.getFloat("KH", "w0", 0.1);
       delta = cm.getFloat("KH", "delta", 0.03);
     }
+  }
+};
+
+// the ndraw uniform numbers of a cell: the reference's OpenMP stream (default) or the counter-based generator
+struct KHRandom {
+  const Geo& g;
+  const HydroParams& p;
+  long seed;
+  std::vector<KokkosPoolStream> ks; // empty: hashed generator
+  KHRandom(const Geo& g_, const HydroParams& p_, const KH& kh, int ndraw) : g(g_), p(p_), seed(kh.seed)
+  {
+    if (kh.p_rand && !kh.hash_rng)
+      ks.emplace_back(g, (uint64_t)(kh.seed * (long)(p.myRank + 1)), kh_rand_threads(), ndraw);
+  }
+  double operator()(int i, int j, int k, int d) const
+  {
+    if (!ks.empty())
+      return ks[0](g, i, j, k, d);
+    const uint64_t key = ((uint64_t)seed << 40) ^ (global_cell(g, p, i, j, k) * 4);
+    return hashed_uniform(key + (uint64_t)d);
   }
 };
 
@@ -87,6 +198,7 @@ bool init_kelvin_helmholtz(const HydroParams& p, const ConfigMap& cm, double* U)
   const KH kh(cm);
   const double gamma0 = p.settings.gamma0;
   const double ampl = kh.amplitude, pressure = kh.pressure;
+  const KHRandom rnd(g, p, kh, g.dim);
   for_each_cell(g, [&](int i, int j, int k) {
     const double x = g.x(i), y = g.y(j);
     const size_t o = g.at(i, j, k);
@@ -95,9 +207,8 @@ bool init_kelvin_helmholtz(const HydroParams& p, const ConfigMap& cm, double* U)
       if (kh.p_rand) {
         double d, u, v;
         if (yn < 0.25 || yn > 0.75) { d = kh.d_out; u = kh.vflow_out; v = 0.0; } else { d = kh.d_in; u = kh.vflow_in; v = 0.0; }
-        const uint64_t key = ((uint64_t)kh.seed << 40) ^ (global_cell(g, p, i, j, k) * 4);
-        u += ampl * (hashed_uniform(key) - 0.5);
-        v += ampl * (hashed_uniform(key + 1) - 0.5);
+        u += ampl * (rnd(i, j, k, 0) - 0.5);
+        v += ampl * (rnd(i, j, k, 1) - 0.5);
         U[o + g.sv * ID] = d;
         U[o + g.sv * IU] = d * u;
         U[o + g.sv * IV] = d * v;
@@ -120,10 +231,9 @@ bool init_kelvin_helmholtz(const HydroParams& p, const ConfigMap& cm, double* U)
       if (kh.p_rand) {
         double d, u, v = 0.0, w = 0.0;
         if (zn < 0.25 || zn > 0.75) { d = kh.d_out; u = kh.vflow_out; } else { d = kh.d_in; u = kh.vflow_in; }
-        const uint64_t key = ((uint64_t)kh.seed << 40) ^ (global_cell(g, p, i, j, k) * 4);
-        u += ampl * (hashed_uniform(key) - 0.5);
-        v += ampl * (hashed_uniform(key + 1) - 0.5);
-        w += ampl * (hashed_uniform(key + 2) - 0.5);
+        u += ampl * (rnd(i, j, k, 0) - 0.5);
+        v += ampl * (rnd(i, j, k, 1) - 0.5);
+        w += ampl * (rnd(i, j, k, 2) - 0.5);
         U[o + g.sv * ID] = d;
         U[o + g.sv * IU] = d * u;
         U[o + g.sv * IV] = d * v;
@@ -423,6 +533,7 @@ bool init_mhd_kelvin_helmholtz(const HydroParams& p, const ConfigMap& cm, double
   const double ampl = kh.amplitude, pressure = kh.pressure;
   const double PI = 3.141592653589793238462643383279502884L; // PI_F (real_type.h)
   const double bx = 0.5, by = 0.0, bz = 0.0;
+  const KHRandom rnd(g, p, kh, g.dim);
   for_each_cell(g, [&](int i, int j, int k) {
     const double x = g.x(i), y = g.y(j);
     const size_t o = g.at(i, j, k);
@@ -431,9 +542,8 @@ bool init_mhd_kelvin_helmholtz(const HydroParams& p, const ConfigMap& cm, double
       double d, u, v;
       if (kh.p_rand) {
         if (yn < 0.25 || yn > 0.75) { d = kh.d_out; u = kh.vflow_out; v = 0.0; } else { d = kh.d_in; u = kh.vflow_in; v = 0.0; }
-        const uint64_t key = ((uint64_t)kh.seed << 40) ^ (global_cell(g, p, i, j, k) * 4);
-        u += ampl * (hashed_uniform(key) - 0.5);
-        v += ampl * (hashed_uniform(key + 1) - 0.5);
+        u += ampl * (rnd(i, j, k, 0) - 0.5);
+        v += ampl * (rnd(i, j, k, 1) - 0.5);
       } else if (kh.p_sine_rob) {
         const int n = kh.mode;
         const double y1 = 0.25, y2 = 0.75, rho1 = kh.d_in, rho2 = kh.d_out, v1 = kh.vflow_in, v2 = kh.vflow_out;
@@ -464,10 +574,9 @@ bool init_mhd_kelvin_helmholtz(const HydroParams& p, const ConfigMap& cm, double
         // the 3-D MHD functor leaves the magnetic field at zero in this branch (MHDInitFunctors3D.h:623-660)
         double d, u, v = 0.0, w = 0.0;
         if (zn < 0.25 || zn > 0.75) { d = kh.d_out; u = kh.vflow_out; } else { d = kh.d_in; u = kh.vflow_in; }
-        const uint64_t key = ((uint64_t)kh.seed << 40) ^ (global_cell(g, p, i, j, k) * 4);
-        u += ampl * (hashed_uniform(key) - 0.5);
-        v += ampl * (hashed_uniform(key + 1) - 0.5);
-        w += ampl * (hashed_uniform(key + 2) - 0.5);
+        u += ampl * (rnd(i, j, k, 0) - 0.5);
+        v += ampl * (rnd(i, j, k, 1) - 0.5);
+        w += ampl * (rnd(i, j, k, 2) - 0.5);
         U[o + g.sv * ID] = d;
         U[o + g.sv * IU] = d * u;
         U[o + g.sv * IV] = d * v;
