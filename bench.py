@@ -478,7 +478,10 @@ def run_reference_arm(args):
     if rank != 0:
         return
     w = WORKLOADS[args.workload]
-    n_sample = {"hydro3d": 160, "hydro3d_grav": 160, "mhd": 128, "hydro2d": None, "mhd2d": 1024}[w["fam"]]
+    # 3-D: 256^3 (the reference's MHD work arrays take ~1.7 KB per cell: 29 GB of host memory; 3-4 s per sample on 16 cores)
+    n_sample = {"hydro3d": 256, "hydro3d_grav": 256, "mhd": 256, "hydro2d": None, "mhd2d": 1024}[w["fam"]]
+    if getattr(args, "ref_sample_n", None) and n_sample is not None:
+        n_sample = args.ref_sample_n
     nsteps = {"hydro3d": 3, "hydro3d_grav": 3, "mhd": 2, "hydro2d": 20, "mhd2d": 5}[w["fam"]]
     vals, desc, threads = [], "", 0
     t_all = time.time()
@@ -577,6 +580,8 @@ def main():
     ap.add_argument("--n", "--size", dest="n", type=int, default=None, help="cubic interior size per GPU (default 512); use --size under torchrun, whose own parser claims --n")
     ap.add_argument("--shape", default=None, help="per-GPU interior box NX,NY,NZ of a 3-D workload (overrides --n)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-sample-n", type=int, default=None,
+                    help="--impl reference: cubic size of the bounded sample each step runs (default 256 for the 3-D workloads)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the hydro blast 512^3 line reported under 'secondary'")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

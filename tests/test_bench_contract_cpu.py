@@ -21,7 +21,7 @@ def test_reference_arm_prints_one_json_line():
 
     if not O.have_reference():
         pytest.skip("oracle/_ref is not built here")
-    r = _run("--impl", "reference", "--steps", "1", "--warmup", "0")
+    r = _run("--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-sample-n", "128")  # default sample: 256^3 (29 GB, ~30 s here)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1, r.stdout
