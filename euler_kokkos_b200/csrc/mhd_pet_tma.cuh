@@ -35,7 +35,7 @@ namespace ek {
 #endif
 constexpr int PT_TX = 32, PT_TY = EK_PET_TY, PT_NS = EK_PET_NSTAGE, PT_MINB = EK_PET_MINB;
 static_assert(PT_NS == 1 || PT_NS == 2, "one or two staging buffers");
-constexpr int PT_BX = PT_TX + 2, PT_BY = PT_TY + 2, PT_BOX = PT_BX * PT_BY;  // 34 x 18 cells: tile + 1-cell ring
+constexpr int PT_BX = PT_TX + 2, PT_BY = PT_TY + 2, PT_BOX = PT_BX * PT_BY;  // tile + 1-cell ring (34 x 14 cells)
 constexpr int PT_TILES = (PT_BOX + 31) / 32;                                  // AoSoA tiles per plane of the ring
 constexpr int PT_QPLANE = PT_TILES * 8 * 32, PT_EPLANE = PT_TILES * 3 * 32;   // doubles
 constexpr int PT_RX = 36, PT_RY = PT_BY + 1;                                  // staged box: columns i0-2 .. i0+33 (the box start must be

@@ -4,8 +4,9 @@
 // instead of three each keeps the hot code inside the instruction cache (ncu on the fully inlined version: 72 KB of
 // SASS, 0.93 stall cycles per issued instruction waiting for instruction fetch, 0.13 with the calls).
 // Variants that were measured and lost (round 1, recorded in DESIGN.md section 4.2): a cp.async software pipeline that
-// staged the next problem's inputs in shared memory (+25 % instructions, 38.3 vs 29.5 ms), L2 prefetch of S some planes
-// ahead, warps of a CTA on consecutive planes, fully inlined solvers.
+// staged the next problem's inputs in shared memory (+25 % instructions, 38.3 vs 29.5 ms), per-line L2 prefetch
+// instructions for S some planes ahead (the bulk form below, one instruction per warp, is what pays), warps of a CTA on
+// consecutive planes, fully inlined solvers.
 #pragma once
 #include "mhd_cells.cuh"
 
