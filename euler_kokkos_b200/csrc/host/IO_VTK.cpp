@@ -89,6 +89,11 @@ std::string save_vti(const double* U, const HydroParams& params, const ConfigMap
   std::ofstream out(filename.c_str(), std::ios_base::out | std::ios_base::binary);
   if (!out)
     return std::string();
+  // [output] outputVtkAscii=true: the data arrays as text (operator<< of a double: 6 significant digits), the file then
+  // is a well-formed XML document and starts with the XML declaration (IO_VTK.cpp:91-94, 118-152, 289-292, 316-358)
+  const bool ascii = configMap.getBool("output", "outputVtkAscii", false);
+  if (ascii)
+    out << "<?xml version=\"1.0\"?>\n";
   // global cell extents of this piece; the origin is the global one (the pieces are placed by their extents)
   const int x0 = params.myMpiPos[0] * nx, y0 = params.myMpiPos[1] * ny, z0 = three_d ? params.myMpiPos[2] * nz : 0;
   const double ox = params.xmin, oy = params.ymin, oz = params.zmin;
@@ -107,6 +112,25 @@ std::string save_vti(const double* U, const HydroParams& params, const ConfigMap
   }
   out << "    <PointData>\n";
   out << "    </PointData>\n";
+  const int k0 = three_d ? gw : 0;
+  if (ascii) {
+    out << "    <CellData>\n";
+    for (int iVar = 0; iVar < nbvar; ++iVar) {
+      out << "    <DataArray type=\"Float64\" Name=\"" << variables_names.at(iVar) << "\" format=\"ascii\" >\n";
+      for (int k = k0; k < k0 + nz; ++k)
+        for (int j = gw; j < gw + ny; ++j) {
+          const double* src = U + sv * iVar + (size_t)k * isize * jsize + (size_t)j * isize + gw;
+          for (int i = 0; i < nx; ++i)
+            out << src[i] << " ";
+        }
+      out << "\n    </DataArray>\n";
+    }
+    out << "    </CellData>\n";
+    out << "  </Piece>\n";
+    out << "  </ImageData>\n";
+    out << "</VTKFile>\n";
+    return filename;
+  }
   out << "    <CellData>\n";
   const uint64_t nbytes = (uint64_t)nx * ny * nz * sizeof(double);
   for (int iVar = 0; iVar < nbvar; ++iVar)
@@ -117,8 +141,6 @@ std::string save_vti(const double* U, const HydroParams& params, const ConfigMap
   out << "  </ImageData>\n";
   out << "  <AppendedData encoding=\"raw\">\n";
   out << "_";
-  std::vector<double> row((size_t)nx);
-  const int k0 = three_d ? gw : 0;
   for (int iVar = 0; iVar < nbvar; ++iVar) {
     out.write(reinterpret_cast<const char*>(&nbytes), sizeof(uint64_t));
     for (int k = k0; k < k0 + nz; ++k)

@@ -166,11 +166,6 @@ const std::vector<double>& SolverMusclB200::host_state()
 // SolverHydroMuscl::save_solution_impl (SolverHydroMuscl.h:751-762) -> save_VTK_{2D,3D}
 void SolverMusclB200::save_solution_impl()
 {
-  if (configMap.getBool("output", "outputVtkAscii", false)) {
-    // the reference's ascii branch (IO_VTK.cpp:306-338) is not provided: refuse rather than write another format
-    fprintf(stderr, "[euler_b200] output/outputVtkAscii=true is not supported (raw appended Float64 only)\n");
-    std::exit(EXIT_FAILURE);
-  }
   timers[TIMER_IO]->start();
   finish_pending_output(); // at most one dump in flight: its buffer and the device snapshot are reused
   if (m_async_io && !m_io_buf) {

@@ -206,3 +206,30 @@ def test_decomposed_dump_is_a_pvti_collection_of_the_single_domain_dump(tmp_path
     assert names == names1 and got.shape == ref.shape
     assert np.array_equal(got, ref)
     assert np.array_equal(ref, interior_of(U1, p0.ghost, p0.dim))
+
+
+ASCII_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ascii_vti")
+
+
+@pytest.mark.parametrize("name", ["implode2d", "blast3d", "ot2d", "ot3d"])
+def test_ascii_vti_dump_is_byte_identical_to_the_reference(name, tmp_path):
+    """[output] outputVtkAscii=true (IO_VTK.cpp:91-152, 289-358): XML declaration, one text DataArray per variable, values
+    through operator<< (6 significant digits), interior cells in (k, j, i) order.  The host layer's writer, fed its own
+    initial condition, reproduces dump 0 of the reference binary byte for byte (tests/golden/make_ascii_vti_fixture.py)."""
+    import json
+
+    from euler_kokkos_b200 import hostapi
+
+    with open(os.path.join(ASCII_DIR, "cases.json")) as f:
+        meta = json.load(f)
+    ini = tmp_path / "case.ini"
+    ini.write_text(meta[name]["ini"].replace("@OUTDIR@", str(tmp_path)))
+    case = hostapi.Case(str(ini))
+    U, _ = case.new_state()
+    path = case.save_vti(U, 0)
+    with open(path, "rb") as f:
+        ours = f.read()
+    with open(os.path.join(ASCII_DIR, name + ".vti"), "rb") as f:
+        ref = f.read()
+    assert ours.startswith(b'<?xml version="1.0"?>\n')
+    assert ours == ref

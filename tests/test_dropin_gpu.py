@@ -145,8 +145,10 @@ def test_asynchronous_output_writes_the_same_files():
     assert blobs["yes"] == blobs["no"]
 
 
-def test_restart_and_ascii_output_are_refused():
-    """configurations the drop-in cannot honour stop with an error instead of silently doing something else"""
+def test_restart_is_refused_and_ascii_output_is_written():
+    """a configuration the drop-in cannot honour (restart: HDF5 loaders absent) stops with an error instead of silently
+    doing something else; [output] outputVtkAscii=true writes the reference's text format (byte-compared with the
+    reference binary on the CPU tier: test_abi_and_host.py::test_ascii_vti_dump_is_byte_identical_to_the_reference)"""
     z = np.load(os.path.join(HERE, "golden", "implode2d_hllc.npz"))
     with tempfile.TemporaryDirectory() as td:
         ini = os.path.join(td, "case.ini")
@@ -159,7 +161,12 @@ def test_restart_and_ascii_output_are_refused():
         with open(ini, "w") as f:
             f.write(text)
         r = subprocess.run([BIN, ini], cwd=td, capture_output=True, text=True, timeout=120)
-        assert r.returncode != 0 and "outputVtkAscii" in r.stderr
+        assert r.returncode == 0, r.stderr[-1000:]
+        files = sorted(glob.glob(os.path.join(td, "*.vti")))
+        assert files
+        with open(files[0], "rb") as f:
+            blob = f.read()
+        assert blob.startswith(b'<?xml version="1.0"?>\n') and b'format="ascii"' in blob and b"AppendedData" not in blob
 
 
 def test_shipped_brio_wu_3d_z_asks_for_impl_2_and_is_refused_loudly():
