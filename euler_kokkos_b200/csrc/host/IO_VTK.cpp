@@ -46,14 +46,15 @@ void write_pvti_header(const std::string& headerFilename, const std::string& out
       cx = r / my;
       cy = r % my;
     }
-    out << "    <Piece Extent=\"" << cx * nx << " " << cx * nx + nx << " " << cy * ny << " " << cy * ny + ny << " ";
+    // (the reference indents the pieces of a 3-D file by one blank and those of a 2-D file by four, IO_VTK.cpp:951, :986)
+    out << (three_d ? " " : "    ") << "<Piece Extent=\"" << cx * nx << " " << cx * nx + nx << " " << cy * ny << " " << cy * ny + ny << " ";
     if (three_d)
       out << cz * nz << " " << cz * nz + nz << " ";
     else
       out << 0 << " " << 1;
     out << "\" Source=\"" << piece << "\"/>\n";
   }
-  out << "  </PImageData>\n";
+  out << "</PImageData>\n";
   out << "</VTKFile>\n";
 }
 
@@ -103,12 +104,13 @@ std::string save_vti(const double* U, const HydroParams& params, const ConfigMap
     out << "  <ImageData WholeExtent=\"" << x0 << " " << x0 + nx << " " << y0 << " " << y0 + ny << " " << z0 << " " << z0 + nz << "\" "
         << "Origin=\"" << ox << " " << oy << " " << oz << "\" "
         << "Spacing=\"" << params.dx << " " << params.dy << " " << params.dz << "\">\n";
-    out << "  <Piece Extent=\"" << x0 << " " << x0 + nx << " " << y0 << " " << y0 + ny << " " << z0 << " " << z0 + nz << " " << "\">\n";
+    // (the serial writers leave a blank before the closing quote, the MPI piece writers do not: IO_VTK.cpp:311-312 vs :753-754)
+    out << "  <Piece Extent=\"" << x0 << " " << x0 + nx << " " << y0 << " " << y0 + ny << " " << z0 << " " << z0 + nz << (pieces ? "" : " ") << "\">\n";
   } else {
     out << "  <ImageData WholeExtent=\"" << x0 << " " << x0 + nx << " " << y0 << " " << y0 + ny << " " << 0 << " " << 0 << "\" "
         << "Origin=\"" << ox << " " << oy << " " << 0 << "\" "
         << "Spacing=\"" << params.dx << " " << params.dy << " " << 0 << "\">\n";
-    out << "  <Piece Extent=\"" << x0 << " " << x0 + nx << " " << y0 << " " << y0 + ny << " " << 0 << " " << 0 << " " << "\">\n";
+    out << "  <Piece Extent=\"" << x0 << " " << x0 + nx << " " << y0 << " " << y0 + ny << " " << 0 << " " << 0 << (pieces ? "" : " ") << "\">\n";
   }
   out << "    <PointData>\n";
   out << "    </PointData>\n";

@@ -233,3 +233,39 @@ def test_ascii_vti_dump_is_byte_identical_to_the_reference(name, tmp_path):
         ref = f.read()
     assert ours.startswith(b'<?xml version="1.0"?>\n')
     assert ours == ref
+
+
+def test_pvti_header_and_piece_headers_follow_the_reference_text(tmp_path):
+    """The reference's MPI build cannot run here (no MPI in the image), so the parallel-VTK text has no fixture; this
+    test restates write_pvti_header (IO_VTK.cpp:862-1008) and the piece header of save_VTK_3D_mpi (:737-757) line by
+    line -- including their quirks: pieces of a 3-D .pvti indented by ONE blank (four in 2-D), extents of a 3-D piece
+    followed by a blank inside the quotes, </PImageData> not indented, no blank before the closing quote of the piece
+    file's <Piece Extent> (the serial writers have one) -- and compares it with what the host layer writes."""
+    from euler_kokkos_b200 import hostapi
+
+    ov = {"mesh.nx": 6, "mesh.ny": 5, "mesh.nz": 4, "output.outputdir": str(tmp_path), "output.outputprefix": "p"}
+    cases = [hostapi.Case(hostapi.settings("test_implode_3D.ini"), ov, rank=r, nranks=2) for r in range(2)]
+    assert tuple(cases[0].mpi_dims) == (1, 1, 2)
+    for c in cases:
+        U, _ = c.new_state()
+        c.save_vti(U, 7)
+    names = ["rho", "energy", "rho_vx", "rho_vy", "rho_vz"]
+    exp = ['<?xml version="1.0"?>',
+           '<VTKFile type="PImageData" version="1.0" byte_order="LittleEndian" header_type="UInt64">',
+           '  <PImageData WholeExtent="0 6 0 5 0 8" GhostLevel="0" Origin="0 0 0" Spacing="0.166667 0.2 0.125">',
+           '    <PCellData Scalars="Scalars_">']
+    exp += ['      <PDataArray type="Float64" Name="%s"/>' % n for n in names]
+    exp += ['    </PCellData>',
+            ' <Piece Extent="0 6 0 5 0 4 " Source="p_time0000007_mpi00000.vti"/>',
+            ' <Piece Extent="0 6 0 5 4 8 " Source="p_time0000007_mpi00001.vti"/>',
+            '</PImageData>', '</VTKFile>', '']
+    with open(tmp_path / "p_time0000007.pvti") as f:
+        assert f.read() == "\n".join(exp)
+    with open(tmp_path / "p_time0000007_mpi00001.vti", "rb") as f:
+        head = f.read(600).decode("latin1")
+    exp_piece = ['<VTKFile type="ImageData" version="1.0" byte_order="LittleEndian" header_type="UInt64">',
+                 '  <ImageData WholeExtent="0 6 0 5 4 8" Origin="0 0 0" Spacing="0.166667 0.2 0.125">',
+                 '  <Piece Extent="0 6 0 5 4 8">',
+                 '    <PointData>', '    </PointData>', '    <CellData>',
+                 '     <DataArray type="Float64" Name="rho" format="appended" offset="0" />']
+    assert head.startswith("\n".join(exp_piece) + "\n"), head
