@@ -166,6 +166,11 @@ const std::vector<double>& SolverMusclB200::host_state()
 // SolverHydroMuscl::save_solution_impl (SolverHydroMuscl.h:751-762) -> save_VTK_{2D,3D}
 void SolverMusclB200::save_solution_impl()
 {
+  // [output] vtk_enabled=no: IO_ReadWrite::save_data writes nothing then (IO_ReadWrite.cpp:37, 85-92; the HDF5 / PnetCDF
+  // writers it would call instead are not part of this build); the "Output results" line and the dump counter of
+  // SolverBase::save_solution stay
+  if (!configMap.getBool("output", "vtk_enabled", true))
+    return;
   timers[TIMER_IO]->start();
   finish_pending_output(); // at most one dump in flight: its buffer and the device snapshot are reused
   if (m_async_io && !m_io_buf) {
